@@ -1,0 +1,294 @@
+/*
+ * mdseg.h — C ABI of libmdseg_b200.so
+ *
+ * B200 (sm_100a) implementation of the per-pixel multi-dataset label-space hot
+ * path of Mrhonor/Mul-Datasets-Semantic-Segmentation.  The reference has no
+ * FFI of its own (it is pure Python on ATen); every entry point below cites the
+ * reference lines whose work it replaces.  SURVEY.md §8(b) is the contract.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, enums.  No torch / C++ types cross this ABI.
+ *   - every pointer is a DEVICE pointer unless the parameter says "host".
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - the library never allocates or frees device memory and never
+ *     synchronises the host; the caller owns every buffer.
+ *   - return value: 0 = OK, non-zero = error; text via mdseg_last_error().
+ *   - data errors found on the device (labels outside [0,C) ∪ {ignore}) set
+ *     bits in a caller-owned int32 `err_flag` (may be NULL) — the reference
+ *     would hit a device assert inside nll_loss / a reshape error in bincount.
+ */
+#ifndef MDSEG_H_
+#define MDSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDSEG_VERSION 100 /* 0.1.0 */
+
+/* element types */
+enum {
+  MDSEG_F32 = 0,
+  MDSEG_BF16 = 1,
+  MDSEG_F16 = 2,
+  MDSEG_U8 = 10,
+  MDSEG_I32 = 11,
+  MDSEG_I64 = 12
+};
+
+/* logits layouts */
+enum { MDSEG_NCHW = 0, MDSEG_NHWC = 1 };
+
+/* err_flag bits */
+enum {
+  MDSEG_ERR_LABEL_RANGE = 1, /* label not in [0,C) and != ignore          */
+  MDSEG_ERR_PRED_RANGE = 2,  /* prediction not in [0,Cb)                  */
+  MDSEG_ERR_TOPK_RANGE = 4,  /* n_min larger than the number of loss px   */
+  MDSEG_ERR_DATASET_ID = 8   /* dataset id outside [0,n_datasets)         */
+};
+
+#define MDSEG_MAX_DATASETS 32
+
+/*
+ * OHEM selection state of one "segment" (= one call of the reference's
+ * OhemCELoss / MdsOhemCELoss).  Lives in device memory, caller-allocated,
+ * 128 bytes.  Zeroed by mdseg_ohem_begin; filled by the *_fwd kernels;
+ * completed by mdseg_ohem_select; consumed by the *_bwd kernels.  The layout is
+ * public so tests can read it back.
+ */
+typedef struct mdseg_ohem_state {
+  unsigned long long n_valid; /* #{label != ignore}             (ohem_ce_loss.py:25,52) */
+  unsigned long long n_hard;  /* #{loss > thresh}               (ohem_ce_loss.py:30,74) */
+  unsigned long long n_px;    /* number of loss entries of this segment               */
+  unsigned long long n_min;   /* n_valid / 16                                          */
+  unsigned long long n_sel;   /* |S| : number of selected entries                      */
+  unsigned long long n_gt;    /* top-k mode: #{loss > kth}                             */
+  double sum_hard;            /* Σ loss over {loss > thresh}                           */
+  double sum_sel;             /* Σ loss over S                                         */
+  float thresh;               /* τ = -log(thresh_prob)                                 */
+  float kth;                  /* top-k mode: the n_min-th largest loss                 */
+  float inv_n_sel;            /* 1/|S| (0 if S empty)                                  */
+  float loss;                 /* mean over S (NaN if S empty, like torch.mean([]))     */
+  unsigned int mode;          /* 0 = threshold set, 1 = top-k fallback                 */
+  unsigned int tie_quota;     /* top-k mode: how many entries == kth belong to S       */
+  unsigned int tie_taken;     /* select: ties examined so far (first-come hand-out)    */
+  unsigned int n_ties;        /* top-k mode: #{loss == kth}                            */
+  unsigned int reserved[8];
+} mdseg_ohem_state;
+
+/*
+ * Where the low-resolution logits of image b live, for the fused
+ * upsample+CE kernels.  Passed BY VALUE from the host.  Image b of dataset
+ * d = dataset_ids[b] (d = 0 when dataset_ids == NULL) reads
+ *     base[d] + b * image_stride[d]          (elements, layout [C[d], h, w])
+ * - main multi-dataset loss: every base[d] is the projected-logit buffer
+ *   (loss_cross_datasets.py:1006), C[d] = n_cats of dataset d;
+ * - aux heads: base[d] = aux_logits[d] ([ΣB, C_d, h, w], all images;
+ *   loss_cross_datasets.py:1051).
+ * seg_per_dataset != 0 -> OHEM segment of image b is d (aux heads: one
+ * selection per dataset, :1053-1056), else segment 0 (MdsOhemCELoss: one
+ * selection over the whole batch, ohem_ce_loss.py:70-88).
+ */
+typedef struct mdseg_src_table {
+  const void* base[MDSEG_MAX_DATASETS];
+  long long image_stride[MDSEG_MAX_DATASETS];
+  int C[MDSEG_MAX_DATASETS];
+  int n_datasets;
+  int dtype;           /* MDSEG_F32 / BF16 / F16 */
+  int seg_per_dataset; /* 0 / 1 */
+  int reserved;
+} mdseg_src_table;
+
+/*
+ * Sparse bipartite / remap matrix G [C_ds, C_uni] of one dataset in CSR (rows
+ * = dataset classes) and CSC (columns = unified classes) form, device
+ * resident.  vals may be NULL (all ones: the 0/1 graphs of the SEG stage and
+ * ClassRemap.getRemapMatrix, class_remap.py:176-183).
+ */
+typedef struct mdseg_sparse_graph {
+  const int* csr_ptr;    /* [C_ds + 1]  */
+  const int* csr_col;    /* [nnz] unified ids, ascending within a row */
+  const float* csr_val;  /* [nnz] or NULL */
+  const int* csc_ptr;    /* [C_uni + 1] */
+  const int* csc_row;    /* [nnz] dataset classes, ascending within a column */
+  const float* csc_val;  /* [nnz] or NULL */
+  const float* dense;    /* [C_ds, C_uni] row-major or NULL; when non-NULL the
+                            dense kernels are used (GNN stage) */
+  int C_ds;
+  int nnz;
+  int col_onehot;        /* every column has at most one entry (UOT / pretrain graphs,
+                            ltbgnn_direct_learn.py:426-439,689-692) */
+  int reserved;
+} mdseg_sparse_graph;
+
+typedef struct mdseg_graph_table {
+  mdseg_sparse_graph g[MDSEG_MAX_DATASETS];
+  int n_datasets;
+  int C_uni;
+} mdseg_graph_table;
+
+/* ---- library ---------------------------------------------------------- */
+int mdseg_version(void);
+/* thread-local, valid until the next failing call on this thread */
+const char* mdseg_last_error(void);
+/* number of SMs of the current device (cached) — grids are sized from it */
+int mdseg_sm_count(void);
+
+/* ---- a1 / a2: LUT remap -------------------------------------------------
+ * out[p] = lut[in[p]];  values outside [0,255] (int inputs) map to `oob`.
+ * Replaces `label = self.lb_map[label]` (lib/base_dataset.py:81-82) and the
+ * per-class masked writes of ClassRemap.SingleSegRemapping / SegRemapping /
+ * ReverseSegRemap (lib/class_remap.py:34-66,189-203), which are 256-entry
+ * LUTs.  in_dtype / out_dtype ∈ {U8, I32, I64}. */
+int mdseg_lut_remap(const void* in, int in_dtype, void* out, int out_dtype,
+                    const uint8_t* lut256, int oob, int64_t n, void* stream);
+
+/* ---- a12: confusion matrix ----------------------------------------------
+ * hist[l*Cb + q] += 1 for every p with l = (lut ? lut[label[p]] : label[p])
+ * != ignore, q = pred[p].  hist is int64 [Ca*Cb], accumulated into.
+ * Replaces evaluate.py:89-93,174-181 (np.bincount(label[keep]*C+pred[keep]))
+ * and the rectangular variants evaluate.py:631-634,1738-1741. */
+int mdseg_confusion(const void* label, int label_dtype, const void* pred,
+                    int pred_dtype, const uint8_t* lut256, int64_t* hist,
+                    int Ca, int Cb, int ignore, int64_t n, int32_t* err_flag,
+                    void* stream);
+
+/* ---- a13: IoU from the histogram (device, no sync) ------------------------
+ * iou[c] = h[c,c] / (Σ_r h[r,c] + Σ_q h[c,q] - h[c,c]) (NaN when 0/0) and
+ * miou = nanmean(iou).  evaluate.py:94-98. */
+int mdseg_miou(const int64_t* hist, int C, float* iou, float* miou,
+               void* stream);
+
+/* ---- a8: OHEM state -------------------------------------------------------*/
+size_t mdseg_ohem_state_bytes(void);
+/* workspace for mdseg_ohem_select, per segment */
+size_t mdseg_select_workspace_bytes(int n_segments);
+/* zero n_segments states and set their threshold τ = -log(thresh_prob) given
+ * as the already-computed float `thresh` (ohem_ce_loss.py:17,42). */
+int mdseg_ohem_begin(mdseg_ohem_state* states, int n_segments, float thresh,
+                     void* stream);
+
+/* ---- a7 + first half of a8: full-resolution CE forward --------------------
+ * loss_px[p] = logsumexp_c(z[p,:]) - z[p,label[p]]   (0 where label == ignore)
+ * lse_px[p]  = logsumexp (natural log), kept for the backward.
+ * Accumulates n_valid / n_hard / sum_hard / n_px into states[0].
+ * Replaces nn.CrossEntropyLoss(ignore_index=255, reduction='none') and the
+ * `loss > thresh` compare of lib/loss/ohem_ce_loss.py:25-30. */
+int mdseg_ohem_ce_fwd(const void* logits, int dtype, int layout,
+                      const void* labels, int label_dtype, int N, int C, int H,
+                      int W, int ignore, float* loss_px, float* lse_px,
+                      mdseg_ohem_state* state, int32_t* err_flag, void* stream);
+
+/* ---- second half of a8: selection ------------------------------------------
+ * For each segment: n_min = n_valid/16; S = {loss > τ}; if |S| < n_min, S =
+ * the n_min largest entries (radix select over the fp32 bit pattern, no
+ * sort); loss_out[seg] = mean over S.  image_seg (device int32 [n_images]) maps
+ * an image to its segment (NULL: all images belong to segment 0; entries < 0
+ * or >= n_segments are skipped).  In top-k mode the entries equal to the k-th
+ * value that do not fit into S are overwritten in loss_px with the next
+ * smaller float, so that the backward kernels can test `loss >= kth`.
+ * Replaces ohem_ce_loss.py:30-34 / :74-90. */
+int mdseg_ohem_select(float* loss_px, int n_images, int64_t px_per_image,
+                      const int32_t* image_seg, mdseg_ohem_state* states,
+                      int n_segments, void* workspace, float* loss_out,
+                      int32_t* err_flag, void* stream);
+
+/* ---- a9: full-resolution CE backward ----------------------------------------
+ * dlogits[p,c] = grad_out * w_p * (softmax(z[p,:])_c - [c == label_p]),
+ * w_p = 1/|S| for p in S else 0.  grad_out: device float scalar (AMP scale).
+ * dlogits has the dtype / layout of logits and is fully overwritten. */
+int mdseg_ohem_ce_bwd(const void* logits, int dtype, int layout,
+                      const void* labels, int label_dtype, int N, int C, int H,
+                      int W, int ignore, const float* loss_px,
+                      const float* lse_px, mdseg_ohem_state* state,
+                      const float* grad_out, float grad_scale, void* dlogits,
+                      void* stream);
+
+/* ---- a5: bipartite projection (sparse 0/1 or weighted graphs) ----------------
+ * y[b, n, :, :] = Σ_c G_d[n, c] * x[b, c, :, :], d = dataset_ids[b].
+ * x: [n_images, C_uni, h, w] (dtype), y: fp32 [n_images, y_cmax, h, w] (only
+ * the first C_ds(d) channels of image b are written).
+ * Replaces torch.einsum('bchw,nc->bnhw', logits[dataset_ids==i], bi_graphs[i])
+ * (lib/loss/loss_cross_datasets.py:1006; lib/models/semseg.py:344). */
+int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table* graphs /*host*/,
+                   const int32_t* dataset_ids, int n_images, int h, int w,
+                   float* y, int y_cmax, int32_t* err_flag, void* stream);
+
+/* dx[b, c, :, :] = Σ_n G_d[n, c] * (dyA[b, n] + dyB[b, n]); dyB may be NULL.
+ * dx has dtype of x and is fully overwritten (zeros for images whose dataset
+ * id is out of range). */
+int mdseg_proj_bwd(const float* dyA, const float* dyB, int y_cmax,
+                   const mdseg_graph_table* graphs /*host*/,
+                   const int32_t* dataset_ids, int n_images, int h, int w,
+                   void* dx, int dtype, void* stream);
+
+/* d bi_graph (GNN stage): dG_d[n, c] += Σ_{b in d} Σ_px (dyA+dyB)[b,n,px] * x[b,c,px]
+ * dG: fp32 [n_datasets][dg_stride] with row-major [C_ds, C_uni] inside, must be
+ * zeroed by the caller. */
+int mdseg_proj_bwd_graph(const void* x, int dtype, const float* dyA,
+                         const float* dyB, int y_cmax,
+                         const mdseg_graph_table* graphs /*host*/,
+                         const int32_t* dataset_ids, int n_images, int h, int w,
+                         float* dG, long long dg_stride, void* stream);
+
+/* ---- a6 + a7 (+ a10): fused bilinear upsample (align_corners=True) + CE -------
+ * For every label pixel (Y,X) of image b: interpolate the C low-res logits of
+ * the image's source (see mdseg_src_table) to (Y,X) exactly as
+ * F.interpolate(mode='bilinear', align_corners=True) does
+ * (loss_cross_datasets.py:1007), then per-pixel CE as in mdseg_ohem_ce_fwd.
+ * The [B,C,H,W] upsampled tensor is never materialised.
+ * labels: [n_images, H, W]; loss_px / lse_px: fp32 [n_images*H*W]. */
+int mdseg_up_ce_fwd(const mdseg_src_table* src /*host*/, const int32_t* dataset_ids,
+                    const void* labels, int label_dtype, int n_images, int h,
+                    int w, int H, int W, int ignore, float* loss_px,
+                    float* lse_px, mdseg_ohem_state* states, int32_t* err_flag,
+                    void* stream);
+
+/* Adjoint: gradient w.r.t. the low-res logits.  Written as two fp32 planes with
+ * the layout of the source (base/stride/C taken from `dst`, dtype must be F32):
+ * plane A holds the contributions through the upper interpolation row, plane B
+ * through the lower one; their sum is the gradient (mdseg_proj_bwd and
+ * mdseg_add_planes consume them).  Both planes are fully overwritten for every
+ * image whose dataset id is valid.  grad_out (device, may be NULL = 1) holds one
+ * float per OHEM segment: grad_out[d] when src->seg_per_dataset, else grad_out[0]. */
+int mdseg_up_ce_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset_ids,
+                    const void* labels, int label_dtype, int n_images, int h,
+                    int w, int H, int W, int ignore, const float* loss_px,
+                    const float* lse_px, mdseg_ohem_state* states,
+                    const float* grad_out, float grad_scale,
+                    const mdseg_src_table* dstA /*host*/,
+                    const mdseg_src_table* dstB /*host*/, void* stream);
+
+/* out = a + b converted to out_dtype (aux heads: dlogits_aux = A + B) */
+int mdseg_add_planes(const float* a, const float* b, void* out, int out_dtype,
+                     int64_t n, void* stream);
+
+/* ---- a11: eval probability accumulation ---------------------------------------
+ * probs[c, Y, X] (+)= softmax_c(upsample(logits)[., Y, X]); `first` != 0
+ * overwrites instead of accumulating; `flip` != 0 mirrors the low-res logits
+ * along W first (evaluate.py:165-171).  h==H && w==W is the ori_scales=False
+ * case (no interpolation, evaluate.py:156-164).  One image per call. */
+int mdseg_eval_accum(const void* logits, int dtype, int C, int h, int w,
+                     float* probs, int H, int W, int flip, int first,
+                     void* stream);
+
+/* pred[p] = argmax_c probs[c, p] (first maximal index, like torch.argmax on
+ * distinct values); optionally fused with the confusion matrix update
+ * (label/hist may be NULL).  evaluate.py:172-181. */
+int mdseg_argmax_hist(const float* probs, int C, int64_t n_px, int64_t* pred,
+                      const void* label, int label_dtype, const uint8_t* lut256,
+                      int64_t* hist, int ignore, int32_t* err_flag,
+                      void* stream);
+
+/* legacy 'nearest' resize of a label map (evaluate.py:156-157):
+ * src = min(floor(dst * (in/out)), in-1), scale in fp32. */
+int mdseg_label_nearest(const void* in, int dtype, int Hin, int Win, void* out,
+                        int Hout, int Wout, int n_images, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDSEG_H_ */

@@ -1,0 +1,164 @@
+// lut_remap.cu — 256-entry label LUT gather.
+//
+// Reference work replaced:
+//   label = self.lb_map[label]                      lib/base_dataset.py:81-82
+//   mask[labels==k] = v[j] for every (k, v)         lib/class_remap.py:39-48,55-64
+//   Remap_pred[preds==lb] = k                       lib/class_remap.py:189-203
+// Each of these is out[p] = lut[in[p]] with a uint8[256] table; values outside
+// [0,255] (only possible for int32/int64 inputs) map to `oob`.
+//
+// HBM-bound byte kernel: 16 elements per thread per iteration, 128-bit
+// loads/stores on both sides, LUT staged once per CTA in shared memory.
+// Algorithmic bytes per pixel: sizeof(in) + sizeof(out).
+#include "common.cuh"
+
+namespace mdseg {
+namespace {
+
+constexpr int kE = 16;  // elements per thread per iteration
+
+template <typename T> struct Pack16;
+
+template <> struct Pack16<uint8_t> {
+  static constexpr int kVecs = 1;
+  static __device__ __forceinline__ void unpack(const int4* v, int (&x)[kE]) {
+    const uint32_t w[4] = {(uint32_t)v[0].x, (uint32_t)v[0].y, (uint32_t)v[0].z, (uint32_t)v[0].w};
+#pragma unroll
+    for (int i = 0; i < kE; ++i) x[i] = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
+  }
+  static __device__ __forceinline__ void pack(const int (&x)[kE], int4* v) {
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < kE; ++i) w[i >> 2] |= ((uint32_t)x[i] & 0xffu) << (8 * (i & 3));
+    v[0] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+};
+template <> struct Pack16<int32_t> {
+  static constexpr int kVecs = 4;
+  static __device__ __forceinline__ void unpack(const int4* v, int (&x)[kE]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int a = v[j].x, b = v[j].y, c = v[j].z, d = v[j].w;
+      x[4 * j + 0] = ((unsigned)a < 256u) ? a : -1;
+      x[4 * j + 1] = ((unsigned)b < 256u) ? b : -1;
+      x[4 * j + 2] = ((unsigned)c < 256u) ? c : -1;
+      x[4 * j + 3] = ((unsigned)d < 256u) ? d : -1;
+    }
+  }
+  static __device__ __forceinline__ void pack(const int (&x)[kE], int4* v) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = make_int4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+  }
+};
+template <> struct Pack16<int64_t> {
+  static constexpr int kVecs = 8;
+  static __device__ __forceinline__ void unpack(const int4* v, int (&x)[kE]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[2 * j + 0] = (v[j].y == 0 && (unsigned)v[j].x < 256u) ? v[j].x : -1;
+      x[2 * j + 1] = (v[j].w == 0 && (unsigned)v[j].z < 256u) ? v[j].z : -1;
+    }
+  }
+  static __device__ __forceinline__ void pack(const int (&x)[kE], int4* v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = make_int4(x[2 * j], x[2 * j] >> 31, x[2 * j + 1], x[2 * j + 1] >> 31);
+  }
+};
+
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) lut_remap_kernel(const In* __restrict__ in, Out* __restrict__ out,
+                                                       const uint8_t* __restrict__ lut, int oob, int64_t n) {
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+
+  const int64_t nvec = n / kE;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    int4 a[Pack16<In>::kVecs];
+    const int4* src = reinterpret_cast<const int4*>(in + v * kE);
+#pragma unroll
+    for (int j = 0; j < Pack16<In>::kVecs; ++j) a[j] = ldg_stream_v4(src + j);
+    int x[kE];
+    Pack16<In>::unpack(a, x);
+#pragma unroll
+    for (int i = 0; i < kE; ++i) x[i] = (x[i] >= 0) ? (int)s_lut[x[i]] : oob;
+    int4 o[Pack16<Out>::kVecs];
+    Pack16<Out>::pack(x, o);
+    int4* dst = reinterpret_cast<int4*>(out + v * kE);
+#pragma unroll
+    for (int j = 0; j < Pack16<Out>::kVecs; ++j) stg_stream_v4(dst + j, o[j]);
+  }
+  // ragged tail (< 16 elements)
+  const int64_t t0 = nvec * kE + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 < n) {
+    long long xv = (long long)in[t0];
+    out[t0] = (Out)((xv >= 0 && xv < 256) ? (int)s_lut[xv] : oob);
+  }
+}
+
+// Unaligned fallback: one element per thread.
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) lut_remap_scalar_kernel(const In* __restrict__ in, Out* __restrict__ out,
+                                                              const uint8_t* __restrict__ lut, int oob, int64_t n) {
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long xv = (long long)in[i];
+    out[i] = (Out)((xv >= 0 && xv < 256) ? (int)s_lut[xv] : oob);
+  }
+}
+
+template <typename In, typename Out>
+int launch(const void* in, void* out, const uint8_t* lut, int oob, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+  const int sms = sm_count();
+  if (aligned) {
+    int64_t nvec = n / kE;
+    int64_t blocks = ceil_div64(nvec > 0 ? nvec : 1, 256);
+    int64_t cap = (int64_t)sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    lut_remap_kernel<In, Out><<<(unsigned)blocks, 256, 0, st>>>((const In*)in, (Out*)out, lut, oob, n);
+  } else {
+    int64_t blocks = ceil_div64(n, 256);
+    int64_t cap = (int64_t)sms * 8;
+    if (blocks > cap) blocks = cap;
+    lut_remap_scalar_kernel<In, Out><<<(unsigned)blocks, 256, 0, st>>>((const In*)in, (Out*)out, lut, oob, n);
+  }
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+
+template <typename In>
+int dispatch_out(const void* in, void* out, int out_dtype, const uint8_t* lut, int oob, int64_t n, cudaStream_t st) {
+  switch (out_dtype) {
+    case MDSEG_U8: return launch<In, uint8_t>(in, out, lut, oob, n, st);
+    case MDSEG_I32: return launch<In, int32_t>(in, out, lut, oob, n, st);
+    case MDSEG_I64: return launch<In, int64_t>(in, out, lut, oob, n, st);
+  }
+  set_error("mdseg_lut_remap: unsupported out_dtype %d", out_dtype);
+  return 2;
+}
+
+}  // namespace
+}  // namespace mdseg
+
+extern "C" int mdseg_lut_remap(const void* in, int in_dtype, void* out, int out_dtype, const uint8_t* lut256,
+                               int oob, int64_t n, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(n >= 0, "mdseg_lut_remap: n < 0");
+  MDSEG_REQUIRE(n == 0 || (in && out && lut256), "mdseg_lut_remap: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (in_dtype) {
+    case MDSEG_U8: return dispatch_out<uint8_t>(in, out, out_dtype, lut256, oob, n, st);
+    case MDSEG_I32: return dispatch_out<int32_t>(in, out, out_dtype, lut256, oob, n, st);
+    case MDSEG_I64: return dispatch_out<int64_t>(in, out, out_dtype, lut256, oob, n, st);
+  }
+  set_error("mdseg_lut_remap: unsupported in_dtype %d", in_dtype);
+  return 2;
+}

@@ -1,0 +1,529 @@
+"""Torch-facing operators over the C ABI (``native.py``).
+
+PyTorch is plumbing here: it owns device memory, streams and autograd
+bookkeeping; every computation on the path is a hand-written sm_100a kernel in
+libmdseg_b200.so.  Nothing in this module synchronises the host except
+``check_errors`` (explicit) and the graph cache (only when a bipartite graph
+tensor changed).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import native as N
+
+_DT = {
+    torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16,
+    torch.uint8: N.U8, torch.int32: N.I32, torch.int64: N.I64,
+}
+STATE_BYTES = C.sizeof(N.OhemState)
+assert STATE_BYTES == 128 == N.lib.mdseg_ohem_state_bytes()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mdseg_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _labels(lb):
+    """Labels as a contiguous u8 / i32 / i64 tensor (reference labels are int64, transform_cv2.py:300)."""
+    if lb.dtype not in (torch.uint8, torch.int32, torch.int64):
+        lb = lb.long()
+    return lb.contiguous()
+
+
+# ---- lazily checked device-side data errors -----------------------------------
+_err_flags = {}
+
+
+def err_flag(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _err_flags:
+        _err_flags[key] = torch.zeros(1, dtype=torch.int32, device=f"cuda:{key}")
+    return _err_flags[key]
+
+
+def check_errors(device=None):
+    """Host sync.  Raises if any kernel since the last check saw a bad label / prediction / dataset id
+    (the reference would have hit a device assert in nll_loss or a reshape error after np.bincount)."""
+    flag = err_flag(device if device is not None else torch.cuda.current_device())
+    v = int(flag.item())
+    if v:
+        flag.zero_()
+        names = [n for n, bit in (("label out of range", 1), ("prediction out of range", 2),
+                                  ("top-k larger than the loss vector", 4), ("dataset id out of range", 8)) if v & bit]
+        raise RuntimeError("mdseg_b200 device-side data error: " + ", ".join(names))
+
+
+def read_states(states):
+    """Copy OHEM state(s) to the host (sync) as a list of native.OhemState — for tests / logging."""
+    raw = states.detach().cpu().numpy().tobytes()
+    n = len(raw) // STATE_BYTES
+    return [N.OhemState.from_buffer_copy(raw[i * STATE_BYTES:(i + 1) * STATE_BYTES]) for i in range(n)]
+
+
+# ---- a1 / a2: LUT remap ----------------------------------------------------------
+def lut_remap(x, lut, out_dtype=None, oob=255):
+    """out = lut[x] with a uint8[256] table (lib/base_dataset.py:81-82, lib/class_remap.py:34-66)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    if x.dtype not in (torch.uint8, torch.int32, torch.int64):
+        raise TypeError(f"lut_remap: unsupported input dtype {x.dtype}")
+    out_dtype = out_dtype or x.dtype
+    lut = torch.as_tensor(lut).to(device=x.device, dtype=torch.uint8).contiguous()
+    if lut.numel() != 256:
+        raise ValueError("lut must have 256 entries")
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    N.call("mdseg_lut_remap", _ptr(x), _DT[x.dtype], _ptr(out), _DT[out_dtype], _ptr(lut), int(oob), x.numel(),
+           _stream())
+    return out
+
+
+# ---- a12 / a13: confusion matrix, mIoU ---------------------------------------------
+def confusion(label, pred, n_a, n_b=None, lut=None, ignore=255, hist=None):
+    """hist[l, p] += 1 for label != ignore (evaluate.py:89-93).  int64 [n_a, n_b], accumulated in place."""
+    _require_cuda(label, pred)
+    n_b = n_b or n_a
+    label = _labels(label)
+    pred = _labels(pred)
+    if label.numel() != pred.numel():
+        raise ValueError("label / pred size mismatch")
+    if hist is None:
+        hist = torch.zeros(n_a, n_b, dtype=torch.int64, device=label.device)
+    if lut is not None:
+        lut = torch.as_tensor(lut).to(device=label.device, dtype=torch.uint8).contiguous()
+    N.call("mdseg_confusion", _ptr(label), _DT[label.dtype], _ptr(pred), _DT[pred.dtype], _ptr(lut), _ptr(hist),
+           int(n_a), int(n_b), int(ignore), label.numel(), _ptr(err_flag(label.device)), _stream())
+    return hist
+
+
+def miou(hist):
+    """(iou[C], miou) from an int64 [C, C] histogram, on the device (evaluate.py:94-98)."""
+    _require_cuda(hist)
+    Cn = hist.shape[0]
+    iou = torch.empty(Cn, dtype=torch.float32, device=hist.device)
+    m = torch.empty((), dtype=torch.float32, device=hist.device)
+    N.call("mdseg_miou", _ptr(hist.contiguous()), Cn, _ptr(iou), _ptr(m), _stream())
+    return iou, m
+
+
+# ---- OHEM state helpers ----------------------------------------------------------------
+def _new_states(n, thresh, device):
+    st = torch.empty(n * STATE_BYTES, dtype=torch.uint8, device=device)
+    N.call("mdseg_ohem_begin", _ptr(st), n, float(thresh), _stream())
+    return st
+
+
+def _select(loss_px, n_images, px_per_image, image_seg, states, n_seg):
+    ws = torch.empty(N.lib.mdseg_select_workspace_bytes(n_seg), dtype=torch.uint8, device=loss_px.device)
+    out = torch.empty(n_seg, dtype=torch.float32, device=loss_px.device)
+    N.call("mdseg_ohem_select", _ptr(loss_px), n_images, px_per_image, _ptr(image_seg), _ptr(states), n_seg, _ptr(ws),
+           _ptr(out), _ptr(err_flag(loss_px.device)), _stream())
+    return out
+
+
+def _grad_scalar(g, n=1):
+    g = g.detach().to(torch.float32).reshape(-1).contiguous()
+    assert g.numel() == n
+    return g
+
+
+# ---- a7-a9: OhemCELoss on full-resolution logits -------------------------------------------
+class _OhemCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, thresh, ignore):
+        _require_cuda(logits, labels)
+        if logits.dim() != 4:
+            raise ValueError("logits must be [N, C, H, W]")
+        Nn, Cc, H, W = logits.shape
+        if logits.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            logits = logits.float()
+        if logits.is_contiguous():
+            layout = N.NCHW
+        elif logits.is_contiguous(memory_format=torch.channels_last):
+            layout = N.NHWC
+        else:
+            logits, layout = logits.contiguous(), N.NCHW
+        labels = _labels(labels)
+        if labels.numel() != Nn * H * W:
+            raise ValueError(f"labels {tuple(labels.shape)} do not match logits {tuple(logits.shape)}")
+        dev = logits.device
+        P = Nn * H * W
+        loss_px = torch.empty(P, dtype=torch.float32, device=dev)
+        lse_px = torch.empty(P, dtype=torch.float32, device=dev)
+        st = _new_states(1, thresh, dev)
+        N.call("mdseg_ohem_ce_fwd", _ptr(logits), _DT[logits.dtype], layout, _ptr(labels), _DT[labels.dtype], Nn, Cc,
+               H, W, int(ignore), _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(err_flag(dev)), _stream())
+        out = _select(loss_px, Nn, H * W, None, st, 1)
+        ctx.save_for_backward(logits, labels, loss_px, lse_px, st)
+        ctx.meta = (layout, int(ignore))
+        ctx.states = st
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, labels, loss_px, lse_px, st = ctx.saved_tensors
+        layout, ignore = ctx.meta
+        Nn, Cc, H, W = logits.shape
+        g = _grad_scalar(grad_out)
+        dl = torch.empty_like(logits)  # preserves the memory format
+        N.call("mdseg_ohem_ce_bwd", _ptr(logits), _DT[logits.dtype], layout, _ptr(labels), _DT[labels.dtype], Nn, Cc,
+               H, W, ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, _ptr(dl), _stream())
+        return dl, None, None, None
+
+
+def ohem_ce(logits, labels, thresh, ignore=255):
+    """mean over the OHEM set of CE(logits, labels); `thresh` is already -log(p) (ohem_ce_loss.py:17,21-34)."""
+    return _OhemCE.apply(logits, labels, float(thresh), int(ignore))
+
+
+def ohem_ce_with_state(logits, labels, thresh, ignore=255):
+    """Forward only; returns (loss, loss_px, OhemState) — for tests and logging (host sync)."""
+    with torch.no_grad():
+        class _Ctx:
+            def save_for_backward(self, *a):
+                self.saved = a
+        ctx = _Ctx()
+        loss = _OhemCE.forward(ctx, logits, labels, float(thresh), int(ignore))
+        return loss, ctx.saved[2], read_states(ctx.saved[4])[0]
+
+
+# ---- bipartite graphs: host-side cache of the CSR / CSC device images -------------------------
+class BipartiteGraphs:
+    """Device descriptors of bi_graphs[i] ([C_ds_i, C_uni]) for mdseg_proj_*.
+
+    A graph is stored sparse (CSR + CSC) when at most `dense_frac` of its
+    entries are non-zero and it does not require grad (SEG stage: 0/1 graphs
+    from UOT / pretrain, lib/models/ltbgnn_direct_learn.py:426-439, or
+    ClassRemap.getRemapMatrix, lib/class_remap.py:176-183); otherwise dense (GNN
+    stage).  Rebuilding needs one D2H copy and happens only when the tensor
+    object, its version counter or its storage changed.
+    """
+
+    def __init__(self, dense_frac=0.25):
+        self.dense_frac = dense_frac
+        self._cache = {}
+
+    def _entry(self, i, g):
+        key = (g.data_ptr(), g._version, tuple(g.shape), g.requires_grad, str(g.device))
+        hit = self._cache.get(i)
+        if hit is not None and hit["key"] == key:
+            return hit
+        if g.dim() != 2:
+            raise ValueError("bi_graph must be [C_ds, C_uni]")
+        dev = g.device
+        ent = {"key": key, "C_ds": g.shape[0], "C_uni": g.shape[1]}
+        m = g.detach().to(torch.float32).cpu().numpy()
+        nz = m != 0
+        nnz = int(nz.sum())
+        if g.requires_grad or nnz > self.dense_frac * m.size:
+            ent["dense"] = True
+            ent["nnz"] = nnz
+        else:
+            ent["dense"] = False
+            ent["nnz"] = nnz
+            rows, cols = np.nonzero(nz)  # row-major order: ascending col within a row
+            vals = m[rows, cols]
+            csr_ptr = np.zeros(m.shape[0] + 1, dtype=np.int32)
+            np.cumsum(np.bincount(rows, minlength=m.shape[0]), out=csr_ptr[1:])
+            order = np.lexsort((rows, cols))  # by column, then row
+            csc_ptr = np.zeros(m.shape[1] + 1, dtype=np.int32)
+            np.cumsum(np.bincount(cols, minlength=m.shape[1]), out=csc_ptr[1:])
+            all_ones = bool(np.all(vals == 1.0))
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(dev)
+            ent["csr_ptr"] = t(csr_ptr, np.int32)
+            ent["csr_col"] = t(cols, np.int32)
+            ent["csc_ptr"] = t(csc_ptr, np.int32)
+            ent["csc_row"] = t(rows[order], np.int32)
+            ent["csr_val"] = None if all_ones else t(vals, np.float32)
+            ent["csc_val"] = None if all_ones else t(vals[order], np.float32)
+            ent["col_onehot"] = int(np.all(np.diff(csc_ptr) <= 1))
+        self._cache[i] = ent
+        return ent
+
+    def table(self, graphs):
+        """(GraphTable, keepalive list) for a list of graph tensors."""
+        if len(graphs) > N.MAX_DATASETS:
+            raise ValueError("too many datasets")
+        tab = N.GraphTable()
+        tab.n_datasets = len(graphs)
+        keep = []
+        c_uni = None
+        for i, g in enumerate(graphs):
+            _require_cuda(g)
+            e = self._entry(i, g)
+            c_uni = e["C_uni"] if c_uni is None else c_uni
+            if e["C_uni"] != c_uni:
+                raise ValueError("all graphs must share C_uni")
+            sg = tab.g[i]
+            sg.C_ds, sg.nnz = e["C_ds"], e["nnz"]
+            if e["dense"]:
+                d = g.detach().to(torch.float32).contiguous()
+                keep.append(d)
+                sg.dense = d.data_ptr()
+            else:
+                sg.csr_ptr, sg.csr_col = e["csr_ptr"].data_ptr(), e["csr_col"].data_ptr()
+                sg.csc_ptr, sg.csc_row = e["csc_ptr"].data_ptr(), e["csc_row"].data_ptr()
+                sg.csr_val = _ptr(e["csr_val"])
+                sg.csc_val = _ptr(e["csc_val"])
+                sg.col_onehot = e["col_onehot"]
+                keep.append(e)
+        tab.C_uni = c_uni
+        return tab, keep
+
+
+_default_graphs = BipartiteGraphs()
+
+
+def _ids32(dataset_ids, n, device):
+    if dataset_ids is None:
+        return None
+    ids = torch.as_tensor(dataset_ids, device=device)
+    if ids.numel() != n:
+        raise ValueError("dataset_ids must have one entry per image")
+    return ids.to(torch.int32).contiguous()
+
+
+def _src_table(bases, strides, Cs, dtype, seg_per_dataset):
+    t = N.SrcTable()
+    t.n_datasets = len(bases)
+    t.dtype = dtype
+    t.seg_per_dataset = int(seg_per_dataset)
+    for i, (b, s, c) in enumerate(zip(bases, strides, Cs)):
+        t.base[i] = b
+        t.image_stride[i] = s
+        t.C[i] = c
+    return t
+
+
+# ---- a5 projection alone (model-side eval einsum, semseg.py:342-345) --------------------------------
+def project(logits_uni, graphs, dataset_ids=None, cache=None):
+    """fp32 [B, max C_ds, h, w]: einsum('bchw,nc->bnhw') with the graph of each image's dataset."""
+    _require_cuda(logits_uni)
+    x = logits_uni.contiguous()
+    B, Cu, h, w = x.shape
+    tab, keep = (cache or _default_graphs).table(list(graphs))
+    if tab.C_uni != Cu:
+        raise ValueError(f"graphs have C_uni={tab.C_uni}, logits have {Cu}")
+    cmax = max(g.shape[0] for g in graphs)
+    ids = _ids32(dataset_ids, B, x.device)
+    y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=x.device)
+    N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax,
+           _ptr(err_flag(x.device)), _stream())
+    return y
+
+
+# ---- a5+a6+a7+a8+a9: the fused multi-dataset loss ------------------------------------------------------
+class _MdsProjOhemCE(torch.autograd.Function):
+    """MdsOhemCELoss(project -> upsample -> CE) of loss_cross_datasets.py:1006-1007,1074 in four kernels."""
+
+    @staticmethod
+    def forward(ctx, logits_uni, labels, dataset_ids, thresh, ignore, cache, *graphs):
+        _require_cuda(logits_uni, labels)
+        x = logits_uni
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            x = x.float()
+        x = x.contiguous()
+        B, Cu, h, w = x.shape
+        labels = _labels(labels)
+        if labels.dim() != 3 or labels.shape[0] != B:
+            raise ValueError("labels must be [B, H, W]")
+        H, W = labels.shape[1:]
+        dev = x.device
+        tab, keep = cache.table(list(graphs))
+        if tab.C_uni != Cu:
+            raise ValueError(f"graphs have C_uni={tab.C_uni}, logits have {Cu}")
+        Cs = [g.shape[0] for g in graphs]
+        cmax = max(Cs)
+        ids = _ids32(dataset_ids, B, dev)
+        ef = err_flag(dev)
+        y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=dev)
+        N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, _ptr(ef),
+               _stream())
+        src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, False)
+        P = B * H * W
+        loss_px = torch.empty(P, dtype=torch.float32, device=dev)
+        lse_px = torch.empty(P, dtype=torch.float32, device=dev)
+        st = _new_states(1, thresh, dev)
+        N.call("mdseg_up_ce_fwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, int(ignore),
+               _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(ef), _stream())
+        out = _select(loss_px, B, H * W, None, st, 1)
+        ctx.save_for_backward(x, labels, ids, y, loss_px, lse_px, st, *graphs)
+        ctx.meta = (int(ignore), cache, Cs, cmax, (h, w, H, W))
+        ctx.states = st
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, labels, ids, y, loss_px, lse_px, st, *graphs = ctx.saved_tensors
+        ignore, cache, Cs, cmax, (h, w, H, W) = ctx.meta
+        B, Cu = x.shape[:2]
+        dev = x.device
+        g = _grad_scalar(grad_out)
+        tab, keep = cache.table(list(graphs))
+        n = len(Cs)
+        src = _src_table([y.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+        dyA = torch.empty_like(y)
+        dyB = torch.empty_like(y)
+        dA = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+        dB = _src_table([dyB.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+        N.call("mdseg_up_ce_bwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, ignore,
+               _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dA), C.byref(dB), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            N.call("mdseg_proj_bwd", _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dx),
+                   _DT[x.dtype], _stream())
+        dgs = [None] * n
+        if any(ctx.needs_input_grad[6 + i] for i in range(n)):
+            stride = cmax * Cu
+            dG = torch.zeros(n, stride, dtype=torch.float32, device=dev)
+            N.call("mdseg_proj_bwd_graph", _ptr(x), _DT[x.dtype], _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids),
+                   B, h, w, _ptr(dG), stride, _stream())
+            for i in range(n):
+                if ctx.needs_input_grad[6 + i]:
+                    dgs[i] = dG[i, :Cs[i] * Cu].view(Cs[i], Cu).to(graphs[i].dtype)
+        return (dx, None, None, None, None, None, *dgs)
+
+
+def mds_proj_ohem_ce(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255, cache=None):
+    """One OHEM selection over all images: CE(upsample(project(logits_uni, graph[dataset]))) — no host sync."""
+    return _MdsProjOhemCE.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
+                                *graphs)
+
+
+# ---- a10: per-dataset aux heads (upsample + OhemCE, one selection per dataset) ---------------------------
+class _UpOhemCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, dataset_ids, thresh, ignore, seg_per_dataset, *srcs):
+        labels = _labels(labels)
+        _require_cuda(labels, *srcs)
+        B, H, W = labels.shape
+        dev = labels.device
+        n = len(srcs)
+        dt = srcs[0].dtype
+        if dt not in (torch.float32, torch.bfloat16, torch.float16):
+            dt = torch.float32
+        srcs = [s.to(dt).contiguous() for s in srcs]
+        h, w = srcs[0].shape[2:]
+        for s in srcs:
+            if s.shape[0] != B or tuple(s.shape[2:]) != (h, w):
+                raise ValueError("every source must be [B, C_i, h, w] over all B images")
+        Cs = [s.shape[1] for s in srcs]
+        ids = _ids32(dataset_ids, B, dev) if n > 1 else None
+        src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset)
+        n_seg = n if seg_per_dataset else 1
+        P = B * H * W
+        loss_px = torch.empty(P, dtype=torch.float32, device=dev)
+        lse_px = torch.empty(P, dtype=torch.float32, device=dev)
+        st = _new_states(n_seg, thresh, dev)
+        N.call("mdseg_up_ce_fwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, int(ignore),
+               _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(err_flag(dev)), _stream())
+        out = _select(loss_px, B, H * W, ids if seg_per_dataset else None, st, n_seg)
+        ctx.save_for_backward(labels, ids, loss_px, lse_px, st, *srcs)
+        ctx.meta = (int(ignore), bool(seg_per_dataset), Cs, dt, (h, w, H, W))
+        ctx.states = st
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        labels, ids, loss_px, lse_px, st, *srcs = ctx.saved_tensors
+        ignore, seg_per_dataset, Cs, dt, (h, w, H, W) = ctx.meta
+        B = labels.shape[0]
+        n = len(srcs)
+        n_seg = n if seg_per_dataset else 1
+        g = _grad_scalar(grad_out, n_seg)
+        src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset)
+        # images of other datasets get a zero gradient (their rows are never selected, :1051)
+        dAs = [torch.zeros(s.shape, dtype=torch.float32, device=s.device) for s in srcs]
+        dBs = [torch.zeros(s.shape, dtype=torch.float32, device=s.device) for s in srcs]
+        dA = _src_table([t.data_ptr() for t in dAs], [c * h * w for c in Cs], Cs, N.F32, seg_per_dataset)
+        dB = _src_table([t.data_ptr() for t in dBs], [c * h * w for c in Cs], Cs, N.F32, seg_per_dataset)
+        N.call("mdseg_up_ce_bwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, ignore,
+               _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dA), C.byref(dB), _stream())
+        grads = []
+        for s, a, b in zip(srcs, dAs, dBs):
+            o = torch.empty_like(s)
+            N.call("mdseg_add_planes", _ptr(a), _ptr(b), _ptr(o), _DT[dt], a.numel(), _stream())
+            grads.append(o)
+        return (None, None, None, None, None, *grads)
+
+
+def up_ohem_ce(srcs, labels, dataset_ids, thresh, ignore=255, seg_per_dataset=True):
+    """Per-dataset OhemCE(upsample(srcs[d][ids==d]), labels[ids==d]) as a vector [n_datasets]
+    (seg_per_dataset) or one selection over all images ([1]).  srcs[d]: [B, C_d, h, w] over ALL images."""
+    return _UpOhemCE.apply(labels, dataset_ids, float(thresh), int(ignore), bool(seg_per_dataset), *srcs)
+
+
+def states_of(loss_tensor_fn_ctx):
+    return read_states(loss_tensor_fn_ctx)
+
+
+# ---- a11: evaluator accumulation --------------------------------------------------------------------------
+def eval_accum(logits, probs, flip=False, first=False):
+    """probs[C,H,W] (+)= softmax(upsample_bilinear_ac(logits[C,h,w] (flipped along W if flip)))  (evaluate.py:149-171)."""
+    _require_cuda(logits, probs)
+    if logits.dim() == 4:
+        if logits.shape[0] != 1:
+            raise ValueError("eval_accum takes one image")
+        logits = logits[0]
+    if probs.dim() == 4:
+        probs = probs[0]
+    logits = logits.contiguous()
+    if logits.dtype not in _DT or _DT[logits.dtype] > N.F16:
+        logits = logits.float()
+    Cc, h, w = logits.shape
+    if probs.dtype != torch.float32 or not probs.is_contiguous() or probs.shape[0] != Cc:
+        raise ValueError("probs must be a contiguous fp32 [C, H, W]")
+    H, W = probs.shape[1:]
+    N.call("mdseg_eval_accum", _ptr(logits), _DT[logits.dtype], Cc, h, w, _ptr(probs), H, W, int(flip), int(first),
+           _stream())
+    return probs
+
+
+def argmax_hist(probs, label=None, hist=None, lut=None, ignore=255, want_pred=True):
+    """pred = argmax_c probs; optionally hist[label, pred] += 1 in the same pass (evaluate.py:172-181)."""
+    _require_cuda(probs)
+    if probs.dim() == 4:
+        probs = probs[0]
+    probs = probs.contiguous()
+    Cc = probs.shape[0]
+    n_px = probs[0].numel()
+    pred = torch.empty(probs.shape[1:], dtype=torch.int64, device=probs.device) if want_pred else None
+    lab = None
+    if hist is not None:
+        lab = _labels(label)
+        if lab.numel() != n_px:
+            raise ValueError("label size mismatch")
+        if lut is not None:
+            lut = torch.as_tensor(lut).to(device=probs.device, dtype=torch.uint8).contiguous()
+    N.call("mdseg_argmax_hist", _ptr(probs), Cc, n_px, _ptr(pred), _ptr(lab), _DT[lab.dtype] if lab is not None else 0,
+           _ptr(lut), _ptr(hist), int(ignore), _ptr(err_flag(probs.device)), _stream())
+    return pred
+
+
+def label_nearest(label, size):
+    """Legacy 'nearest' resize of an integer label map [N,H,W] -> [N,h,w] (evaluate.py:156-157)."""
+    _require_cuda(label)
+    label = _labels(label)
+    Nn, Hin, Win = label.shape
+    Ho, Wo = size
+    out = torch.empty(Nn, Ho, Wo, dtype=label.dtype, device=label.device)
+    N.call("mdseg_label_nearest", _ptr(label), _DT[label.dtype], Hin, Win, _ptr(out), Ho, Wo, Nn, _stream())
+    return out
+
+
+def neg_log(p):
+    """-log(p) in fp32, as torch computes OhemCELoss.thresh (ohem_ce_loss.py:17)."""
+    return float(-torch.log(torch.tensor(p, dtype=torch.float)))

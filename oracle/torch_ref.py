@@ -1,0 +1,130 @@
+"""The reference's loss / evaluator call sequence restated with the same torch ops
+(test infrastructure and CPU baseline, see oracle/__init__.py).
+
+Runs on whatever device its inputs live on; on the CPU box it is the
+``cpu_baseline`` that bench.py times, on the GPU box the same functions on CUDA
+tensors are "the reference's eager path on the same B200".
+"""
+import torch
+import torch.nn.functional as F
+
+IGNORE = 255
+
+
+def neg_log_thresh(p):
+    """lib/loss/ohem_ce_loss.py:17 — thresh = -log(tensor(p, dtype=float))."""
+    return -torch.log(torch.tensor(p, dtype=torch.float))
+
+
+def ce_none(logits, labels, ignore=IGNORE):
+    """lib/loss/ohem_ce_loss.py:19,27 — CrossEntropyLoss(ignore_index, reduction='none'), fp32 like autocast does."""
+    return F.cross_entropy(logits.float(), labels.long(), ignore_index=ignore, reduction="none")
+
+
+def ohem_select_mean(loss_vec, n_min, thresh):
+    """lib/loss/ohem_ce_loss.py:30-34 (and :74-90): keep loss > thresh; fewer than n_min -> topk(n_min); mean."""
+    hard = loss_vec[loss_vec > thresh]
+    if hard.numel() < n_min:
+        hard, _ = loss_vec.topk(n_min)
+    return torch.mean(hard)
+
+
+def ohem_ce_loss(logits, labels, thresh_p, ignore=IGNORE):
+    """OhemCELoss.forward, lib/loss/ohem_ce_loss.py:21-34."""
+    thresh = neg_log_thresh(thresh_p).to(logits.device)
+    n_min = labels[labels != ignore].numel() // 16
+    loss = ce_none(logits, labels, ignore).view(-1)
+    return ohem_select_mean(loss, n_min, thresh)
+
+
+def mds_ohem_ce_loss(logits_list, labels, dataset_ids, n_datasets, thresh_p, ignore=IGNORE):
+    """MdsOhemCELoss.forward, lib/loss/ohem_ce_loss.py:48-90: per-dataset CE vectors concatenated in dataset
+    order, ONE selection, n_min from all labels of the batch."""
+    thresh = neg_log_thresh(thresh_p).to(labels.device)
+    n_min = labels[labels != ignore].numel() // 16
+    losses, cur = [], 0
+    for i in range(n_datasets):
+        if not (dataset_ids == i).any():
+            continue
+        losses.append(ce_none(logits_list[cur], labels[dataset_ids == i], ignore).view(-1))
+        cur += 1
+    return ohem_select_mean(torch.cat(losses, dim=0), n_min, thresh)
+
+
+def project(logits, graph):
+    """lib/loss/loss_cross_datasets.py:1006 — einsum('bchw, nc -> bnhw')."""
+    return torch.einsum("bchw, nc -> bnhw", logits, graph)
+
+
+def upsample(x, size):
+    """lib/loss/loss_cross_datasets.py:1007 — bilinear, align_corners=True."""
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+
+
+def multi_dataset_seg_loss(logits_uni, labels, dataset_ids, bi_graphs, thresh_p=0.4, ignore=IGNORE):
+    """The SEG-stage core of CrossDatasetsCELoss_AdvGNN.forward (loss_cross_datasets.py:988-1009,1074):
+    per present dataset project + upsample, then MdsOhemCELoss(0.4)."""
+    n_datasets = len(bi_graphs)
+    size = (labels.size(1), labels.size(2))
+    remap_logits = []
+    for i in range(n_datasets):
+        if not (dataset_ids == i).any():
+            continue
+        remap_logits.append(upsample(project(logits_uni[dataset_ids == i], bi_graphs[i]), size))
+    return mds_ohem_ce_loss(remap_logits, labels, dataset_ids, n_datasets, thresh_p, ignore)
+
+
+def aux_heads_loss(aux_logits, labels, dataset_ids, thresh_p=0.7, ignore=IGNORE):
+    """loss_cross_datasets.py:1044-1056 (is_adv=False branch): Σ_i OhemCELoss(0.7)(upsample(aux[i][ids==i]), target[ids==i])."""
+    size = (labels.size(1), labels.size(2))
+    total = None
+    for i in range(len(aux_logits)):
+        if not (dataset_ids == i).any():
+            continue
+        li = ohem_ce_loss(upsample(aux_logits[i][dataset_ids == i], size), labels[dataset_ids == i], thresh_p, ignore)
+        total = li if total is None else total + li
+    return total
+
+
+def seg_stage_total_loss(logits_uni, aux_logits, labels, dataset_ids, bi_graphs, aux_weight):
+    """loss = MdsOhemCE(0.4) + aux_weight * Σ aux (loss_cross_datasets.py:1074-1080,1129-1130)."""
+    main = multi_dataset_seg_loss(logits_uni, labels, dataset_ids, bi_graphs)
+    aux = aux_heads_loss(aux_logits, labels, dataset_ids)
+    return main + aux_weight * aux, main, aux
+
+
+def remap_matrix_ce_loss(logits, labels, dataset_ids, remap_matrices, ignore=IGNORE):
+    """CrossDatasetsCELoss.forward (loss_cross_datasets.py:323-347): per dataset plain mean CE of the
+    remap-matrix projection, summed — the path the reference's golden value 5.106813430786133 pins."""
+    loss = None
+    for i, m in enumerate(remap_matrices):
+        if not (dataset_ids == i).any():
+            continue
+        li = F.cross_entropy(project(logits[dataset_ids == i], m), labels[dataset_ids == i], ignore_index=ignore)
+        loss = li if loss is None else loss + li
+    return loss
+
+
+# ---- evaluator (evaluate.py:46-99,101-192) ------------------------------------------------
+def eval_probs(logits_passes, size, flips=None):
+    """probs = Σ softmax(upsample(logits)) over passes (evaluate.py:149-171).  `flips[i]` marks passes whose
+    logits come from the mirrored image and are flipped back before the interpolation (:165-170)."""
+    probs = None
+    for i, lg in enumerate(logits_passes):
+        if flips is not None and flips[i]:
+            lg = torch.flip(lg, dims=(3,))
+        if tuple(lg.shape[-2:]) != tuple(size):
+            lg = upsample(lg, size)
+        p = torch.softmax(lg.float(), dim=1)
+        probs = p if probs is None else probs + p
+    return probs
+
+
+def eval_preds(probs):
+    """evaluate.py:172."""
+    return torch.argmax(probs, dim=1)
+
+
+def nearest_label(label, size):
+    """evaluate.py:156-157."""
+    return F.interpolate(label.float().unsqueeze(1), size=size, mode="nearest").squeeze(1).long()
