@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline metric on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the per-pixel multi-dataset label-space path over one synthetic batch:
+    raw uint8 label maps --lb_map LUT--> labels
+    unified logits --bipartite projection + bilinear upsample + OhemCE fwd + selection + bwd--> loss, dlogits
+    (labels, preds) --confusion matrix (+ all-reduce) --> mIoU per dataset
+Metric: labelled pixels / second, whole job (all ranks).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+METRIC = "labelled pixels/sec (head+OHEM fwd+bwd, mIoU hist)"
+UNIT = "pixels/s"
+
+WORKLOADS = {
+    # name: (n_cats, C_uni, dataset ids of the per-GPU batch, (h, w), (H, W))
+    "cfg3": ([19, 64, 37, 19, 26, 150, 133], 358, [0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6], (256, 512), (1024, 2048)),
+    "cfg2": ([19, 12, 36], 67, [0] * 5 + [1] * 5 + [2] * 6, (256, 512), (1024, 2048)),
+    "cfg1": ([19], 19, [0, 0], (128, 256), (512, 1024)),
+    "tiny": ([5, 3, 7], 11, [0, 1, 2, 2], (16, 32), (64, 128)),
+}
+WORKLOAD_NAMES = {
+    "cfg3": "ltbgnn_7_datasets_snp: 7-dataset unified label space (C_uni 358), per-GPU batch 16x1024x2048, logits 256x512",
+    "cfg2": "ltbgnn_city_cam_a2d2: 3 datasets (C_uni 67), per-GPU batch 16x1024x2048, logits 256x512",
+    "cfg1": "bisenetv2_city-sized: 1 dataset 19 classes, batch 2x512x1024, logits 128x256",
+    "tiny": "tiny self-test",
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--label-dtype", default="int64", choices=["int64", "uint8"],
+                    help="dtype of the remapped label maps (the reference's loaders hand int64 to the loss)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-times", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic batch: identical recipe for the GPU arm and the CPU arms
+# ---------------------------------------------------------------------------------------------
+def make_graphs(n_cats, c_uni, gen):
+    graphs = []
+    for c in n_cats:
+        idx = torch.randint(0, c, (c_uni,), generator=gen)
+        idx[:c] = torch.arange(c)  # every dataset class non-empty (column-one-hot 0/1 graph, SEG stage)
+        m = torch.zeros(c, c_uni)
+        m[idx, torch.arange(c_uni)] = 1
+        graphs.append(m)
+    return graphs
+
+
+def make_luts(n_cats):
+    luts = []
+    for c in n_cats:
+        lut = np.full(256, 255, dtype=np.uint8)
+        lut[:243] = np.arange(243) % c  # raw ids 243..255 are void (~5 % ignore)
+        luts.append(lut)
+    return luts
+
+
+def make_batch(workload, device, seed, images=None):
+    n_cats, c_uni, ids, (h, w), (H, W) = WORKLOADS[workload]
+    if images is not None:
+        ids = [ids[i] for i in images]
+    gen = torch.Generator().manual_seed(1234)
+    graphs = make_graphs(n_cats, c_uni, gen)
+    luts = make_luts(n_cats)
+    dgen = torch.Generator(device=device).manual_seed(seed)
+    B = len(ids)
+    x = torch.randn(B, c_uni, h, w, generator=dgen, device=device)
+    raw = torch.randint(0, 256, (B, H, W), generator=dgen, device=device, dtype=torch.uint8)
+    pred = torch.empty(B, H, W, dtype=torch.int64, device=device)
+    for b, d in enumerate(ids):
+        pred[b] = torch.randint(0, n_cats[d], (H, W), generator=dgen, device=device)
+    return dict(n_cats=n_cats, c_uni=c_uni, ids=ids, h=h, w=w, H=H, W=W, x=x, raw=raw, pred=pred, graphs=graphs,
+                luts=luts)
+
+
+def dataset_slices(ids):
+    """contiguous image ranges per dataset (ids are sorted in the trainer's batch layout)."""
+    out, start = [], 0
+    for i in range(1, len(ids) + 1):
+        if i == len(ids) or ids[i] != ids[start]:
+            out.append((ids[start], start, i))
+            start = i
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class Clocks(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, False, []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+KERNELS_PER_CALL = {"mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
+                    "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
+                    "mdseg_proj_bwd": 1, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
+
+
+def run_ours(args, rank, world, local_rank):
+    from mdseg_b200 import native, ops  # raises if libmdseg_b200.so is missing: no fallback
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    launches = {"n": 0}
+    per_call_ms = {}
+    timing = {"on": False}
+    raw_call = native.call
+
+    def counting_call(name, *a):
+        launches["n"] += KERNELS_PER_CALL.get(name, 1)
+        if timing["on"]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            raw_call(name, *a)
+            e1.record()
+            per_call_ms.setdefault(name, []).append((e0, e1))
+        else:
+            raw_call(name, *a)
+
+    native.call = counting_call
+    ops.N.call = counting_call
+
+    bt = make_batch(args.workload, dev, 1234 + rank)
+    n_cats, ids, H, W = bt["n_cats"], bt["ids"], bt["H"], bt["W"]
+    B = len(ids)
+    px = B * H * W
+    lab_dt = torch.int64 if args.label_dtype == "int64" else torch.uint8
+    graphs = [g.to(dev) for g in bt["graphs"]]
+    luts = [torch.from_numpy(l).to(dev) for l in bt["luts"]]
+    ids_t = torch.tensor(ids, dtype=torch.int32, device=dev)
+    slices = dataset_slices(ids)
+    thresh = ops.neg_log(0.4)
+    x = bt["x"].requires_grad_(True)
+    labels = torch.empty(B, H, W, dtype=lab_dt, device=dev)
+    offs = np.cumsum([0] + [c * c for c in n_cats])
+    hist_flat = torch.zeros(int(offs[-1]), dtype=torch.int64, device=dev)
+    hists = [hist_flat[offs[d]:offs[d + 1]].view(n_cats[d], n_cats[d]) for d in range(len(n_cats))]
+    out = {}
+
+    def step(raw, xin, pred):
+        # a1: dataset lb_map LUT (lib/base_dataset.py:81-82), one table per dataset
+        for d, s, e in slices:
+            labels[s:e] = ops.lut_remap(raw[s:e], luts[d], out_dtype=lab_dt)
+        # a5-a9: fused projection + upsample + OhemCE fwd, selection, bwd
+        xin.grad = None
+        loss = ops.mds_proj_ohem_ce(xin, labels, ids_t, graphs, thresh)
+        loss.backward()
+        # a12/a13: confusion matrices + mIoU
+        hist_flat.zero_()
+        for d, s, e in slices:
+            ops.confusion(labels[s:e], pred[s:e], n_cats[d], hist=hists[d])
+        if world > 1:
+            dist.all_reduce(hist_flat)  # one int64 all-reduce for all datasets (evaluate.py:187-188)
+        mious = [ops.miou(hists[d])[1] for d, _, _ in slices]
+        out["loss"], out["miou"] = loss.detach(), torch.stack(mious)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: `value` ---------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(bt["raw"], x, bt["pred"])
+    barrier()
+    ops.check_errors(dev)
+    launches["n"] = 0
+    clocks = Clocks(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(bt["raw"], x, bt["pred"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = launches["n"]
+    clk = clocks.summary() if clocks else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = px * world / (ms_per_step * 1e-3)
+    loss_val = float(out["loss"])
+
+    # ---- end-to-end through the public API with HOST buffers: `e2e` ------------------------------------
+    h_x = bt["x"].detach().cpu().pin_memory()
+    h_raw = bt["raw"].cpu().pin_memory()
+    h_pred = bt["pred"].cpu().pin_memory()
+    d_x = torch.empty_like(bt["x"].detach()).requires_grad_(True)
+    d_raw, d_pred = torch.empty_like(bt["raw"]), torch.empty_like(bt["pred"])
+    h2d = h_x.numel() * h_x.element_size() + h_raw.numel() + h_pred.numel() * 8
+    d2h = 4 + 4 * len(slices)
+
+    def e2e_step():
+        with torch.no_grad():
+            d_x.copy_(h_x, non_blocking=True)
+        d_raw.copy_(h_raw, non_blocking=True)
+        d_pred.copy_(h_pred, non_blocking=True)
+        step(d_raw, d_x, d_pred)
+        return float(out["loss"].cpu()), out["miou"].cpu()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = px * world / (float(t.item()) / e2e_steps * 1e-3)
+    del h_x, d_x
+
+    # ---- per-kernel durations (separate loop, L2 flushed between launches) -> roofline -------------------
+    peak, peak_src = measured_peak()
+    roof, per_kernel = None, {}
+    if rank == 0 and not args.no_kernel_times:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def flushing_call(name, *a):
+            flush.fill_(1)
+            counting_call(name, *a)
+
+        native.call = flushing_call
+        ops.N.call = flushing_call
+        timing["on"] = True
+        for _ in range(5):
+            step(bt["raw"], x, bt["pred"])
+        torch.cuda.synchronize()
+        timing["on"] = False
+        native.call = counting_call
+        ops.N.call = counting_call
+        del flush
+        e = 4 if bt["x"].dtype == torch.float32 else 2
+        L = 8 if lab_dt == torch.int64 else 1
+        cbar = sum(n_cats[d] for d in ids) / len(ids)  # mean C_ds over the images of the batch
+        cu = bt["c_uni"]
+        # algorithmic bytes per LABEL pixel of each C-ABI call; 16 label px per logit px
+        alg = {
+            "mdseg_proj_fwd": (cu * e + cbar * 4) / 16,
+            "mdseg_up_ce_fwd": cbar * 4 / 16 + L + 8,
+            "mdseg_ohem_select": 4,
+            "mdseg_up_ce_bwd": cbar * 4 / 16 + L + 8 + 2 * cbar * 4 / 16,
+            "mdseg_proj_bwd": (2 * cbar * 4 + cu * e) / 16,
+            "mdseg_lut_remap": 1 + L,
+            "mdseg_confusion": L + 8,
+        }
+        for name, evs in per_call_ms.items():
+            calls_per_step = len(evs) / 5
+            tot = sum(a.elapsed_time(b) for a, b in evs) / 5  # ms per step spent in this ABI call
+            per_kernel[name] = {"ms_per_step": round(tot, 4), "launches_per_step": calls_per_step}
+            if name in alg:
+                gbs = alg[name] * px / (tot * 1e-3) / 1e9
+                per_kernel[name].update({"alg_bytes_per_px": round(alg[name], 3), "achieved_gbs": round(gbs, 1),
+                                         "frac": round(gbs / peak, 4)})
+        cand = {k: v for k, v in per_kernel.items() if "achieved_gbs" in v}
+        if cand:
+            top = max(cand, key=lambda k: cand[k]["ms_per_step"])
+            traffic = None
+            prof = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(prof):
+                traffic = json.load(open(prof)).get(top)
+            roof = {"kernel": top, "bound": "hbm", "achieved": cand[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": cand[top]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "duration_ms": cand[top]["ms_per_step"]}
+        # whole group A (3*C_uni*e/16 + 2L + 20 bytes per pixel) and B (L + 8)
+        grpA = sum(per_kernel.get(k, {}).get("ms_per_step", 0) for k in
+                   ("mdseg_proj_fwd", "mdseg_up_ce_fwd", "mdseg_ohem_begin", "mdseg_ohem_select", "mdseg_up_ce_bwd",
+                    "mdseg_proj_bwd"))
+        bytesA = 3 * cu * e / 16 + 2 * L + 20
+        if grpA:
+            per_kernel["group_A_loss_fwd_select_bwd"] = {
+                "ms_per_step": round(grpA, 4), "alg_bytes_per_px": bytesA,
+                "achieved_gbs": round(bytesA * px / (grpA * 1e-3) / 1e9, 1),
+                "frac": round(bytesA * px / (grpA * 1e-3) / 1e9 / peak, 4)}
+
+    res = None
+    if rank == 0:
+        res = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "name": args.workload,
+                       "pixels_per_step_per_gpu": px, "labels": args.label_dtype, "logits": "f32 NCHW",
+                       "bi_graphs": "0/1 column-one-hot (SEG stage)", "ohem_thresh": 0.4,
+                       "l2": "inputs_exceed_l2 (logits %.2f GB, labels+preds %.2f GB per step)" %
+                             (bt["x"].numel() * 4 / 1e9, px * (1 + (8 if lab_dt == torch.int64 else 1) + 8) / 1e9),
+                       "parallelism": f"dp{world} (images sharded, OHEM selection rank-local, one int64 hist all-reduce)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": gpu_launches, "clocks": clk, "loss": loss_val,
+            "roofline": roof, "kernels": per_kernel,
+        }
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms: the oracle's torch restatement of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step(bt):
+    """One pass of the SAME path with the reference's torch ops on CPU tensors (oracle/torch_ref.py)."""
+    from oracle import label_space as ls, torch_ref as tr
+    ids = bt["ids"]
+    ids_t = torch.tensor(ids, dtype=torch.int32)
+    labels = torch.empty(bt["raw"].shape, dtype=torch.int64)
+    for d, s, e in dataset_slices(ids):
+        labels[s:e] = torch.from_numpy(ls.lut_gather(bt["raw"][s:e].numpy(), bt["luts"][d]).astype(np.int64))
+    x = bt["x"].detach().requires_grad_(True)
+    loss = tr.multi_dataset_seg_loss(x, labels, ids_t, bt["graphs"], 0.4)
+    loss.backward()
+    mious = []
+    for d, s, e in dataset_slices(ids):
+        h = ls.confusion(labels[s:e].numpy(), bt["pred"][s:e].numpy(), bt["n_cats"][d])
+        mious.append(ls.ious_miou(h)[1])
+    return float(loss), mious
+
+
+def cpu_sample_images(workload):
+    ids = WORKLOADS[workload][2]
+    if workload in ("cfg3", "cfg2"):
+        return [0, len(ids) // 2]  # two full-resolution images from two different datasets
+    return list(range(len(ids)))
+
+
+def run_cpu(args, steps, warmup):
+    torch.set_num_threads(os.cpu_count())
+    images = cpu_sample_images(args.workload)
+    bt = make_batch(args.workload, "cpu", 1234, images=images)
+    px = len(images) * bt["H"] * bt["W"]
+    for _ in range(warmup):
+        cpu_step(bt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(bt)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"images {images} of the {args.workload} batch at full resolution ({px} px per step), "
+                      f"oracle/torch_ref.py + numpy bincount (the reference's own torch ops), fp32, "
+                      f"{steps} timed step(s) of {dt:.2f} s"}, dt
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, dt = run_cpu(args, steps=max(1, min(args.steps, 3)), warmup=1)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "name": args.workload},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the mdseg hot path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    res = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = run_cpu(args, steps=1, warmup=0 if args.workload in ("cfg3", "cfg2") else 1)
+            res["cpu_baseline"] = cb
+        else:
+            res["cpu_baseline"] = None
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

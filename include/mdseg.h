@@ -96,10 +96,15 @@ typedef struct mdseg_src_table {
   const void* base[MDSEG_MAX_DATASETS];
   long long image_stride[MDSEG_MAX_DATASETS];
   int C[MDSEG_MAX_DATASETS];
+  int C_alloc[MDSEG_MAX_DATASETS]; /* channels allocated per image (>= C; 0 means C) */
   int n_datasets;
   int dtype;           /* MDSEG_F32 / BF16 / F16 */
   int seg_per_dataset; /* 0 / 1 */
-  int reserved;
+  int cmax_ready;      /* cmax already holds the per-pixel channel maximum of the sources */
+  float* cmax;         /* optional workspace, fp32 [n_images, h, w]: max_c src[b, c, y, x].  When
+                          non-NULL (and dtype F32, w % 4 == 0, up-sampling factor <= 5) the
+                          TMA-pipelined kernels are used; mdseg_up_ce_fwd fills it first unless
+                          cmax_ready (mdseg_proj_fwd can produce it for free). */
 } mdseg_src_table;
 
 /*
@@ -215,7 +220,8 @@ int mdseg_ohem_ce_bwd(const void* logits, int dtype, int layout,
  * (lib/loss/loss_cross_datasets.py:1006; lib/models/semseg.py:344). */
 int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table* graphs /*host*/,
                    const int32_t* dataset_ids, int n_images, int h, int w,
-                   float* y, int y_cmax, int32_t* err_flag, void* stream);
+                   float* y, int y_cmax, float* cmax_out /* optional fp32 [n_images,h,w]: max_n y */,
+                   int32_t* err_flag, void* stream);
 
 /* dx[b, c, :, :] = Σ_n G_d[n, c] * (dyA[b, n] + dyB[b, n]); dyB may be NULL.
  * dx has dtype of x and is fully overwritten (zeros for images whose dataset

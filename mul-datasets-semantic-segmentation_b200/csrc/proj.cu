@@ -28,7 +28,7 @@ namespace {
 template <typename T, int PX>
 __global__ void __launch_bounds__(256)
 proj_fwd_sparse_kernel(const T* __restrict__ x, const mdseg_graph_table tab, const int32_t* __restrict__ dataset_ids,
-                       int64_t hw, float* __restrict__ y, int y_cmax, int* err_flag) {
+                       int64_t hw, float* __restrict__ y, int y_cmax, float* __restrict__ cmax, int* err_flag) {
   const int b = blockIdx.y;
   const int d = dataset_ids ? dataset_ids[b] : 0;
   if (d < 0 || d >= tab.n_datasets) {
@@ -42,6 +42,9 @@ proj_fwd_sparse_kernel(const T* __restrict__ x, const mdseg_graph_table tab, con
   const int64_t n_groups = hw / PX;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_groups; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = q * PX;
+    float mx[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) mx[i] = -3.402823466e38f;
     for (int n = 0; n < g.C_ds; ++n) {
       float acc[PX];
 #pragma unroll
@@ -71,6 +74,8 @@ proj_fwd_sparse_kernel(const T* __restrict__ x, const mdseg_graph_table tab, con
         for (int i = 0; i < PX; ++i) acc[i] = fmaf(wv, v[i], acc[i]);
       }
       float* dst = yb + (int64_t)n * hw + p;
+#pragma unroll
+      for (int i = 0; i < PX; ++i) mx[i] = fmaxf(mx[i], acc[i]);
       if constexpr (PX == 1) {
         dst[0] = acc[0];
       } else {
@@ -78,6 +83,10 @@ proj_fwd_sparse_kernel(const T* __restrict__ x, const mdseg_graph_table tab, con
         for (int i = 0; i < PX; i += 4)
           *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
       }
+    }
+    if (cmax) {  // per-pixel channel maximum, the softmax shift of the fused upsample+CE kernels
+#pragma unroll
+      for (int i = 0; i < PX; ++i) cmax[(int64_t)b * hw + p + i] = mx[i];
     }
   }
 }
@@ -336,7 +345,7 @@ int check_table(const mdseg_graph_table* t, const char* who) {
 
 template <typename T>
 int launch_fwd(const void* x, const mdseg_graph_table* t, const int32_t* ids, int n_images, int64_t hw, float* y,
-               int y_cmax, int32_t* ef, cudaStream_t s) {
+               int y_cmax, float* cmax, int32_t* ef, cudaStream_t s) {
   constexpr int PXV = 16 / sizeof(T);
   if (any_sparse(t)) {
     const bool vec = (hw % PXV == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
@@ -345,8 +354,8 @@ int launch_fwd(const void* x, const mdseg_graph_table* t, const int32_t* ids, in
     int64_t want = ceil_div64((int64_t)sm_count() * 8, n_images);
     if (bx > want) bx = want;
     dim3 grid((unsigned)bx, (unsigned)n_images);
-    if (vec) proj_fwd_sparse_kernel<T, PXV><<<grid, 256, 0, s>>>((const T*)x, *t, ids, hw, y, y_cmax, ef);
-    else proj_fwd_sparse_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, *t, ids, hw, y, y_cmax, ef);
+    if (vec) proj_fwd_sparse_kernel<T, PXV><<<grid, 256, 0, s>>>((const T*)x, *t, ids, hw, y, y_cmax, cmax, ef);
+    else proj_fwd_sparse_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, *t, ids, hw, y, y_cmax, cmax, ef);
     MDSEG_LAUNCH_OK();
   }
   if (any_dense(t)) {
@@ -396,7 +405,8 @@ int launch_dgraph(const void* x, const float* dyA, const float* dyB, int y_cmax,
 }  // namespace mdseg
 
 extern "C" int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table* graphs, const int32_t* dataset_ids,
-                              int n_images, int h, int w, float* y, int y_cmax, int32_t* err_flag, void* stream) {
+                              int n_images, int h, int w, float* y, int y_cmax, float* cmax_out, int32_t* err_flag,
+                              void* stream) {
   using namespace mdseg;
   if (int rc = check_table(graphs, "mdseg_proj_fwd")) return rc;
   MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0, "mdseg_proj_fwd: bad shape");
@@ -406,9 +416,9 @@ extern "C" int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table*
   const int64_t hw = (int64_t)h * w;
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case MDSEG_F32: return launch_fwd<float>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, err_flag, s);
-    case MDSEG_BF16: return launch_fwd<__nv_bfloat16>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, err_flag, s);
-    case MDSEG_F16: return launch_fwd<__half>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, err_flag, s);
+    case MDSEG_F32: return launch_fwd<float>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, s);
+    case MDSEG_BF16: return launch_fwd<__nv_bfloat16>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, s);
+    case MDSEG_F16: return launch_fwd<__half>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, s);
   }
   set_error("mdseg_proj_fwd: unsupported dtype %d", dtype);
   return 2;

@@ -30,7 +30,7 @@
 // traffic per label pixel is C*4/16 (low-res logits) + L (label) + 8 (loss, lse).
 #include <float.h>
 
-#include "common.cuh"
+#include "up_ce_internal.cuh"
 
 namespace mdseg {
 namespace {
@@ -40,33 +40,6 @@ constexpr int kRB = 5;    // label rows per register tile
 constexpr int kNB = 5;    // label columns per register tile
 constexpr int kWarps = kCT / 32;
 constexpr int kRowBuf = 32 * kNB;  // per-warp staging row for coalesced stores
-
-struct Geom {
-  AxisMap ym, xm;
-  int h, w, H, W;
-};
-
-// smallest dst in [0, n_out] whose source floor is >= target (n_out if none)
-__device__ __forceinline__ int first_dst_ge(const AxisMap& m, int target, int n_out) {
-  if (target <= 0) return 0;
-  if (target > m.n_in - 1 || m.scale <= 0.f) return n_out;
-  int d = (int)ceilf((float)target / m.scale);
-  d = d < 0 ? 0 : (d > n_out ? n_out : d);
-  while (d > 0 && m.floor_at(d - 1) >= target) --d;
-  while (d < n_out && m.floor_at(d) < target) ++d;
-  return d;
-}
-
-struct SelParams {
-  float thresh, kth, w;
-  unsigned mode;
-};
-// Membership in S is a pure function of the stored loss: in top-k mode
-// mdseg_ohem_select has already demoted the ties that did not make the quota
-// to just below kth, so `loss >= kth` is exact.
-__device__ __forceinline__ bool is_selected(const SelParams& p, float loss) {
-  return p.mode == 0 ? (loss > p.thresh) : (loss >= p.kth);
-}
 
 // Stage classes [c_lo, c_lo+cc) of the two low-res rows (g, y1) and columns
 // [xlo, xlo+fw) (clamped to w-1) into S2[(c*2+r)*fwp + xl], scaled by log2(e).
@@ -115,20 +88,6 @@ __device__ __forceinline__ void channel_max_smem(float* __restrict__ cm, const f
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-struct FwdArgs {
-  mdseg_src_table src;
-  const int32_t* dataset_ids;
-  const void* labels;
-  Geom gm;
-  int ignore;
-  int cc_max;   // classes per staged chunk
-  int fwp;      // smem row pitch
-  float* loss_px;
-  float* lse_px;
-  mdseg_ohem_state* states;
-  int* err_flag;
-};
-
 template <typename T, typename L, int R>
 __device__ __forceinline__ void fwd_rows(const FwdArgs& a, const T* __restrict__ img, int C, int b, int g, int y1,
                                          int Yb, int xlo, int fw, int x, int xl, int Xbeg, int nx, int nx_max,
@@ -357,22 +316,6 @@ up_ce_fwd_kernel(const FwdArgs a) {
 // ---------------------------------------------------------------------------
 // backward (adjoint)
 // ---------------------------------------------------------------------------
-struct BwdArgs {
-  mdseg_src_table src;
-  mdseg_src_table dstA, dstB;
-  const int32_t* dataset_ids;
-  const void* labels;
-  Geom gm;
-  int ignore;
-  int cc_max;
-  int fwp;
-  const float* loss_px;
-  const float* lse_px;
-  mdseg_ohem_state* states;
-  const float* grad_out;
-  float grad_scale;
-};
-
 // One register tile (R rows x <=kNB columns of the thread's cell) against the
 // staged chunk; accumulates into the shared output tile O[(c*2+plane)*fwp + t].
 template <typename T, typename L, int R>
@@ -714,6 +657,10 @@ extern "C" int mdseg_up_ce_fwd(const mdseg_src_table* src, const int32_t* datase
   a.ignore = ignore; a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.err_flag = err_flag;
   a.cc_max = 0; a.fwp = 0;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int rc = up_ce_fwd_tma(a, label_dtype, n_images, s);  // fp32, w % 4 == 0, factor <= 5, cmax workspace
+    if (rc >= 0) return rc;
+  }
   switch (src->dtype) {
     case MDSEG_F32: return fwd_labels<float>(label_dtype, a, n_images, s);
     case MDSEG_BF16: return fwd_labels<__nv_bfloat16>(label_dtype, a, n_images, s);
@@ -742,6 +689,10 @@ extern "C" int mdseg_up_ce_bwd(const mdseg_src_table* src, const int32_t* datase
   a.gm = make_geom(h, w, H, W); a.ignore = ignore; a.loss_px = loss_px; a.lse_px = lse_px; a.states = states;
   a.grad_out = grad_out; a.grad_scale = grad_scale; a.cc_max = 0; a.fwp = 0;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int rc = up_ce_bwd_tma(a, label_dtype, n_images, s);
+    if (rc >= 0) return rc;
+  }
   switch (src->dtype) {
     case MDSEG_F32: return bwd_labels<float>(label_dtype, a, n_images, s);
     case MDSEG_BF16: return bwd_labels<__nv_bfloat16>(label_dtype, a, n_images, s);

@@ -34,7 +34,9 @@ class SrcTable(C.Structure):
         ("base", C.c_void_p * MAX_DATASETS),
         ("image_stride", C.c_longlong * MAX_DATASETS),
         ("C", C.c_int * MAX_DATASETS),
-        ("n_datasets", C.c_int), ("dtype", C.c_int), ("seg_per_dataset", C.c_int), ("reserved", C.c_int),
+        ("C_alloc", C.c_int * MAX_DATASETS),
+        ("n_datasets", C.c_int), ("dtype", C.c_int), ("seg_per_dataset", C.c_int), ("cmax_ready", C.c_int),
+        ("cmax", C.c_void_p),
     ]
 
 
@@ -67,7 +69,7 @@ SIGNATURES = {
     "mdseg_ohem_ce_fwd": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mdseg_ohem_select": (_I, [_P, _I, _L, _P, _P, _I, _P, _P, _P, _P]),
     "mdseg_ohem_ce_bwd": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
-    "mdseg_proj_fwd": (_I, [_P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, _I, _P, _P]),
+    "mdseg_proj_fwd": (_I, [_P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "mdseg_proj_bwd": (_I, [_P, _P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, _I, _P]),
     "mdseg_proj_bwd_graph": (_I, [_P, _I, _P, _P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, C.c_longlong, _P]),
     "mdseg_up_ce_fwd": (_I, [C.POINTER(SrcTable), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -208,22 +208,28 @@ class BipartiteGraphs:
     from UOT / pretrain, lib/models/ltbgnn_direct_learn.py:426-439, or
     ClassRemap.getRemapMatrix, lib/class_remap.py:176-183); otherwise dense (GNN
     stage).  Rebuilding needs one D2H copy and happens only when the tensor
-    object, its version counter or its storage changed.
+    object, its version counter or its storage changed.  The cache keeps a
+    reference to the tensor it was built from, so a recycled allocation can never
+    alias a stale entry; writes that bypass autograd's version counter
+    (``g.data[...] = ``) need an explicit ``invalidate()``.
     """
 
     def __init__(self, dense_frac=0.25):
         self.dense_frac = dense_frac
         self._cache = {}
 
+    def invalidate(self):
+        self._cache.clear()
+
     def _entry(self, i, g):
-        key = (g.data_ptr(), g._version, tuple(g.shape), g.requires_grad, str(g.device))
+        key = (id(g), g.data_ptr(), g._version, tuple(g.shape), g.requires_grad, str(g.device))
         hit = self._cache.get(i)
         if hit is not None and hit["key"] == key:
             return hit
         if g.dim() != 2:
             raise ValueError("bi_graph must be [C_ds, C_uni]")
         dev = g.device
-        ent = {"key": key, "C_ds": g.shape[0], "C_uni": g.shape[1]}
+        ent = {"key": key, "tensor": g, "C_ds": g.shape[0], "C_uni": g.shape[1]}
         m = g.detach().to(torch.float32).cpu().numpy()
         nz = m != 0
         nnz = int(nz.sum())
@@ -295,15 +301,18 @@ def _ids32(dataset_ids, n, device):
     return ids.to(torch.int32).contiguous()
 
 
-def _src_table(bases, strides, Cs, dtype, seg_per_dataset):
+def _src_table(bases, strides, Cs, dtype, seg_per_dataset, c_alloc=None, cmax=None, cmax_ready=False):
     t = N.SrcTable()
     t.n_datasets = len(bases)
     t.dtype = dtype
     t.seg_per_dataset = int(seg_per_dataset)
+    t.cmax = _ptr(cmax)
+    t.cmax_ready = int(cmax_ready)
     for i, (b, s, c) in enumerate(zip(bases, strides, Cs)):
         t.base[i] = b
         t.image_stride[i] = s
         t.C[i] = c
+        t.C_alloc[i] = c_alloc if c_alloc else c
     return t
 
 
@@ -319,7 +328,7 @@ def project(logits_uni, graphs, dataset_ids=None, cache=None):
     cmax = max(g.shape[0] for g in graphs)
     ids = _ids32(dataset_ids, B, x.device)
     y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=x.device)
-    N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax,
+    N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, None,
            _ptr(err_flag(x.device)), _stream())
     return y
 
@@ -349,9 +358,12 @@ class _MdsProjOhemCE(torch.autograd.Function):
         ids = _ids32(dataset_ids, B, dev)
         ef = err_flag(dev)
         y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=dev)
-        N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, _ptr(ef),
-               _stream())
-        src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, False)
+        ymax = torch.empty(B, h, w, dtype=torch.float32, device=dev)  # channel maximum of y: the softmax shift
+        all_sparse = all(not tab.g[i].dense for i in range(len(Cs)))
+        N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, _ptr(ymax),
+               _ptr(ef), _stream())
+        src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, False, c_alloc=cmax,
+                         cmax=ymax, cmax_ready=all_sparse)
         P = B * H * W
         loss_px = torch.empty(P, dtype=torch.float32, device=dev)
         lse_px = torch.empty(P, dtype=torch.float32, device=dev)
@@ -373,7 +385,9 @@ class _MdsProjOhemCE(torch.autograd.Function):
         g = _grad_scalar(grad_out)
         tab, keep = cache.table(list(graphs))
         n = len(Cs)
-        src = _src_table([y.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+        scratch = torch.empty(1, dtype=torch.float32, device=dev)  # non-NULL cmax selects the TMA kernels
+        src = _src_table([y.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False, c_alloc=cmax, cmax=scratch,
+                         cmax_ready=True)
         dyA = torch.empty_like(y)
         dyB = torch.empty_like(y)
         dA = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
@@ -422,7 +436,8 @@ class _UpOhemCE(torch.autograd.Function):
                 raise ValueError("every source must be [B, C_i, h, w] over all B images")
         Cs = [s.shape[1] for s in srcs]
         ids = _ids32(dataset_ids, B, dev) if n > 1 else None
-        src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset)
+        smax = torch.empty(B, h, w, dtype=torch.float32, device=dev) if dt == torch.float32 else None
+        src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset, cmax=smax)
         n_seg = n if seg_per_dataset else 1
         P = B * H * W
         loss_px = torch.empty(P, dtype=torch.float32, device=dev)
@@ -444,7 +459,9 @@ class _UpOhemCE(torch.autograd.Function):
         n = len(srcs)
         n_seg = n if seg_per_dataset else 1
         g = _grad_scalar(grad_out, n_seg)
-        src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset)
+        scratch = torch.empty(1, dtype=torch.float32, device=labels.device) if dt == torch.float32 else None
+        src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset,
+                         cmax=scratch, cmax_ready=True)
         # images of other datasets get a zero gradient (their rows are never selected, :1051)
         dAs = [torch.zeros(s.shape, dtype=torch.float32, device=s.device) for s in srcs]
         dBs = [torch.zeros(s.shape, dtype=torch.float32, device=s.device) for s in srcs]
