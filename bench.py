@@ -159,7 +159,7 @@ class Clocks(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 KERNELS_PER_CALL = {"mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
                     "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
-                    "mdseg_proj_bwd": 1, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
+                    "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 2, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -314,6 +314,7 @@ def run_ours(args, rank, world, local_rank):
             "mdseg_ohem_select": 4,
             "mdseg_up_ce_bwd": cbar * 4 / 16 + L + 8 + 2 * cbar * 4 / 16,
             "mdseg_proj_bwd": (2 * cbar * 4 + cu * e) / 16,
+            "mdseg_mds_bwd": cbar * 4 / 16 + L + 8 + cu * e / 16,
             "mdseg_lut_remap": 1 + L,
             "mdseg_confusion": L + 8,
         }
@@ -338,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
         # whole group A (3*C_uni*e/16 + 2L + 20 bytes per pixel) and B (L + 8)
         grpA = sum(per_kernel.get(k, {}).get("ms_per_step", 0) for k in
                    ("mdseg_proj_fwd", "mdseg_up_ce_fwd", "mdseg_ohem_begin", "mdseg_ohem_select", "mdseg_up_ce_bwd",
-                    "mdseg_proj_bwd"))
+                    "mdseg_proj_bwd", "mdseg_mds_bwd"))
         bytesA = 3 * cu * e / 16 + 2 * L + 20
         if grpA:
             per_kernel["group_A_loss_fwd_select_bwd"] = {

@@ -268,6 +268,24 @@ int mdseg_up_ce_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset_
                     const mdseg_src_table* dstA /*host*/,
                     const mdseg_src_table* dstB /*host*/, void* stream);
 
+/* ---- a9 of the multi-dataset loss in one call --------------------------------------
+ * dx[b, c, :, :] = d loss / d logits_uni for loss = MdsOhemCELoss(upsample(einsum(logits_uni, G_d)))
+ * (autograd replay of lib/loss/loss_cross_datasets.py:1006-1007,1074 + lib/loss/ohem_ce_loss.py:61-90).
+ * `src` describes the PROJECTED low-res logits kept by the forward (fp32 [n_images, C_alloc, h, w]).
+ * Fused route (fp32 sources, column-one-hot sparse graphs, up-sampling factor in [1,5] per axis):
+ * one kernel recomputes the softmax, applies the adjoint of the bilinear interpolation and
+ * broadcasts through G^T into dx; a small fix-up kernel finishes the rows on segment
+ * boundaries.  Otherwise: mdseg_up_ce_bwd into two planes of the workspace + mdseg_proj_bwd.
+ * dx ([n_images, C_uni, h, w], dx_dtype) is fully overwritten.  The workspace is caller-owned
+ * scratch of at least mdseg_mds_bwd_workspace_bytes(...) bytes. */
+size_t mdseg_mds_bwd_workspace_bytes(const mdseg_src_table* src /*host*/, const mdseg_graph_table* graphs /*host*/,
+                                     int n_images, int h, int w, int H, int W);
+int mdseg_mds_bwd(const mdseg_src_table* src /*host*/, const mdseg_graph_table* graphs /*host*/,
+                  const int32_t* dataset_ids, const void* labels, int label_dtype, int n_images, int h, int w,
+                  int H, int W, int ignore, const float* loss_px, const float* lse_px, mdseg_ohem_state* states,
+                  const float* grad_out, float grad_scale, void* dx, int dx_dtype, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 /* out = a + b converted to out_dtype (aux heads: dlogits_aux = A + B) */
 int mdseg_add_planes(const float* a, const float* b, void* out, int out_dtype,
                      int64_t n, void* stream);

@@ -1,0 +1,653 @@
+// mds_bwd.cu — fused backward of  project -> bilinear upsample (align_corners=True) -> OHEM CE
+//  in ONE pass: softmax recompute, adjoint of the interpolation and the
+// broadcast through G^T, written straight into dlogits_uni.
+//
+// Reference work replaced (autograd replay of lib/loss/loss_cross_datasets.py:1006-1007 +
+// lib/loss/ohem_ce_loss.py:61-90): log_softmax_backward over [B_i,C_ds,H,W], upsample_bilinear2d
+// backward (scatter), the einsum backward (bmm) and the index_put into [ΣB,C_uni,h,w].
+//
+// Work decomposition — one WARP per unit, nothing shared between warps (CTA = 32 threads):
+//   unit = (image b, class group of 32 dataset classes, strip of 31 low-res columns,
+//           segment of `seg_rows` cell-rows);  a cell-row g interpolates between low-res rows g, g+1.
+//   lane l owns cell x = 31*strip + l - 1 (lane 0 is the left halo cell) and, for l >= 1, column x.
+//   * the class planes of rows (g, g+1) arrive as 4-D TMA boxes [16 classes][2 rows][36 cols]
+//     in a 3-stage mbarrier ring (lane 0 issues, nobody copies);
+//   * per (pixel, class): w*softmax = ex2(z2 - (lse2 - log2 w)), with the 4..5 x 4..5 label pixels
+//     of the cell in registers and the arithmetic packed two columns per instruction (FFMA2/FADD2);
+//     per class the cell reduces to 4 sums (upper/lower row x own/right column); the right-column
+//     part moves one lane up by shuffle;
+//   * the -w*[c == label] term is a shared-memory scatter per pixel (two phases, no atomics);
+//   * vertical: the lower-row sums of cell-row g are carried in shared memory and added to the
+//     upper-row sums of cell-row g+1, so every low-res row inside a segment is final when it
+//     leaves the warp and is broadcast to the unified channels of its class (CSR walk of G, or the
+//     identity for the aux heads).  Only the first row of a segment is incomplete: its two halves
+//     go to a scratch plane and a small fix-up kernel adds and broadcasts them.
+// Every operand order is fixed, there are no atomics: the gradient is bit-reproducible.
+#include "tma_util.cuh"
+
+namespace mdseg {
+namespace {
+
+using namespace tma;
+
+constexpr int kKC = 16;                         // classes per TMA stage
+constexpr int kBoxW = 36;                       // staged columns: <= 3 alignment + 33
+constexpr int kStages = 2;
+constexpr int kStageFloats = kKC * 2 * kBoxW;   // 1152
+constexpr int kStageBytes = kStageFloats * 4;   // 4608
+constexpr int kCG = 32;                         // classes per unit
+constexpr int kOwn = 31;                        // owned columns per strip
+constexpr int kStgW = 176;                      // staged label columns: <= 15 alignment + 32 cells x 5
+constexpr int kMaxR = 5;
+constexpr int kUMax = 384;                      // CSR entries of one class group cached in shared memory
+
+struct GraphDev {
+  const int* csr_ptr;  // NULL: identity (output channel = class)
+  const int* csr_col;
+  const float* csr_val;
+  const int* csc_ptr;
+};
+
+struct Args {
+  mdseg_src_table src;
+  int src_scaled;  // sources already multiplied by log2(e)
+  const int32_t* dataset_ids;
+  const void* labels;
+  Geom gm;
+  int ignore;
+  const float* loss_px;
+  const float* lse_px;
+  const mdseg_ohem_state* states;
+  const float* grad_out;
+  float grad_scale;
+  void* out_base[MDSEG_MAX_DATASETS];
+  long long out_image_stride[MDSEG_MAX_DATASETS];
+  int out_channels[MDSEG_MAX_DATASETS];
+  GraphDev g[MDSEG_MAX_DATASETS];
+  int zero_invalid;  // images with an out-of-range dataset id get zeros in out_base[0]
+  float* scrA;       // [n_images][n_seg][c_scr][w]: upper-row half of the first row of a segment
+  float* scrB;       // same shape: lower-row half left over by the segment above
+  float* lw2;        // [n_images*H*W]: lse*log2e - log2|w| for pixels with a gradient, +inf otherwise
+  uint8_t* sel8;     // [n_images*H*W]: class of the pixel, 255 = no gradient
+  int c_scr;
+  int seg_rows, n_seg, n_strips;
+};
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- pass 0: selection state of every label pixel in the form the main kernel consumes --------------------
+template <typename L>
+__global__ void __launch_bounds__(256) mds_bwd_prep_kernel(const Args a, int64_t px_per_image) {
+  const int b = blockIdx.y;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  const bool valid_ds = d >= 0 && d < a.src.n_datasets;
+  const int C = valid_ds ? a.src.C[d] : 0;
+  SelParams sp;
+  sp.thresh = 0.f; sp.kth = 0.f; sp.mode = 0; sp.w = 0.f;
+  if (valid_ds) {
+    const mdseg_ohem_state* st = a.states + (a.src.seg_per_dataset ? d : 0);
+    sp.thresh = st->thresh; sp.kth = st->kth; sp.mode = st->mode;
+    sp.w = (a.grad_out ? a.grad_out[a.src.seg_per_dataset ? d : 0] : 1.f) * a.grad_scale * st->inv_n_sel;
+  }
+  const float wabs = fabsf(sp.w);
+  const float log2w = log2f(wabs);
+  const float kInf = __int_as_float(0x7f800000);
+  const L* labels = (const L*)a.labels;
+  const int64_t base = (int64_t)b * px_per_image;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < px_per_image / 4;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = base + q * 4;
+    const float4 ls = *reinterpret_cast<const float4*>(a.loss_px + p);
+    const float4 le = *reinterpret_cast<const float4*>(a.lse_px + p);
+    const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, lev[4] = {le.x, le.y, le.z, le.w};
+    float o[4];
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int lv = load_label<L>(labels, p + i);
+      const bool sel = (lv != a.ignore) && ((unsigned)lv < (unsigned)C) && (wabs > 0.f) && is_selected(sp, lsv[i]);
+      o[i] = sel ? fmaf(lev[i], kLog2e, -log2w) : kInf;
+      packed |= (sel ? (uint32_t)lv : 255u) << (8 * i);
+    }
+    *reinterpret_cast<float4*>(a.lw2 + p) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint32_t*>(a.sel8 + p) = packed;
+  }
+}
+
+// zero rows [r0, r1) (and row h-1 when `last`) of channel u at column x
+template <typename TO>
+__device__ __forceinline__ void zero_rows(const Args& a, TO* outb, int u, int r0, int r1, bool last, int x, bool own) {
+  if (!own) return;
+  const int h = a.gm.h, w = a.gm.w;
+  for (int r = r0; r < r1; ++r) outb[((int64_t)u * h + r) * w + x] = from_f32<TO>(0.f);
+  if (last) outb[((int64_t)u * h + (h - 1)) * w + x] = from_f32<TO>(0.f);
+}
+
+struct Unit {
+  int lane, b, seg, x, xl, sx, nx, c_beg, c_end, n_ch, g0, g1, box_x, n_loads, Xa, wst, p0;
+  bool own, cached;
+  float w_signed, wsign;
+};
+
+// value v of class `cls` (group-relative index cg) at (row, x): broadcast to the output channels of the class
+template <typename TO>
+__device__ __forceinline__ void store_class(const Args& a, const GraphDev& gd, const Unit& un, TO* outb,
+                                            const int* ucol, const int* uptr, int cg, int row, float v) {
+  const int w = a.gm.w;
+  if (gd.csr_ptr == nullptr) {
+    if (un.own) outb[((int64_t)(un.c_beg + cg) * a.gm.h + row) * w + un.x] = from_f32<TO>(v);
+    return;
+  }
+  const int e0 = uptr[cg], e1 = uptr[cg + 1];
+  if (un.cached && gd.csr_val == nullptr) {
+    const TO tv = from_f32<TO>(v);
+    TO* o = outb + (int64_t)row * w + un.x;
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+      const int uh = ucol[e];  // u * h
+      if (un.own) o[(int64_t)uh * w] = tv;
+    }
+  } else {
+    for (int e = e0; e < e1; ++e) {
+      const int u = __ldg(gd.csr_col + un.p0 + e);
+      const float val = gd.csr_val ? __ldg(gd.csr_val + un.p0 + e) : 1.f;
+      if (un.own) outb[((int64_t)u * a.gm.h + row) * w + un.x] = from_f32<TO>(v * val);
+    }
+  }
+}
+
+// lane 0: queue the selection state (lw2 + class byte rows) of cell-row g into shared memory
+__device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int g, float* lw2s, uint8_t* labs,
+                                              uint64_t* sbar) {
+  int Ys, Ye;
+  cell_span(a.gm.ym, g, a.gm.H, Ys, Ye);
+  const int R = Ye - Ys;
+  mbar_expect_tx(sbar, (uint32_t)(R * un.wst * 5));
+  for (int j = 0; j < R; ++j) {
+    const int64_t p = ((int64_t)un.b * a.gm.H + (Ys + j)) * a.gm.W + un.Xa;
+    bulk_g2s(lw2s + j * kStgW, a.lw2 + p, (uint32_t)(un.wst * 4), sbar);
+    bulk_g2s(labs + j * kStgW, a.sel8 + p, (uint32_t)un.wst, sbar);
+  }
+}
+
+// One cell-row: all class chunks of the unit.  RT rows / 4 (+1 when NX5) columns are the compiled loop bounds.
+template <typename TO, int RT, bool NX5>
+__device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, const GraphDev& gd, const Unit& un,
+                                         TO* outb, int g, int R, const float (&l1w)[5], const float (&l1h)[kMaxR],
+                                         float* stages, uint64_t* bars, float4* Oc, float* carry, float* lw2s,
+                                         uint8_t* labs, const int* ucol, const int* uptr) {
+  const int lane = un.lane;
+  const float kInf = __int_as_float(0x7f800000);
+  constexpr int NXT = NX5 ? 5 : 4;
+  // per-pixel exponent offsets and class bytes of this lane's cell, from the staged rows
+  float2 LW[RT][2];
+  float lw4[RT];
+  uint32_t lb[RT], lb4[RT];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    float t[5];
+    uint32_t bytes = 0xffffffffu, b4 = 255u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      t[i] = kInf;
+      if (j < R && i < un.nx) {
+        t[i] = lw2s[j * kStgW + un.sx + i];
+        const uint32_t v = labs[j * kStgW + un.sx + i];
+        if (i < 4) bytes = (bytes & ~(255u << (8 * i))) | (v << (8 * i));
+        else b4 = v;
+      }
+    }
+    LW[j][0] = make_float2(t[0], t[1]);
+    LW[j][1] = make_float2(t[2], t[3]);
+    lw4[j] = t[4];
+    lb[j] = bytes;
+    lb4[j] = b4;
+  }
+  __syncwarp();
+  if (lane == 0 && g + 1 < un.g1) issue_staging(a, un, g + 1, lw2s, labs, &bars[kStages]);
+
+  float2 L1H[RT];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) L1H[j] = dup2(l1h[j]);
+  const float2 L1W[2] = {make_float2(l1w[0], l1w[1]), make_float2(l1w[2], l1w[3])};
+  const float l1w4 = l1w[4];
+  const bool first_partial = (g == un.g0) && (un.g0 > 0);
+
+  for (int k = 0; k < un.n_ch; ++k) {
+    const int q = (g - un.g0) * un.n_ch + k;
+    const int slot = q % kStages;
+    const int c_lo = un.c_beg + k * kKC;
+    const int cc = (un.c_end - c_lo) < kKC ? (un.c_end - c_lo) : kKC;
+
+    // -w*[c == label] per corner, accumulated first into lane-private slots {own-up, right-up, own-low, right-low}
+    for (int c = 0; c < cc; ++c) Oc[c * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      if (j < R) {
+        const float wl = un.w_signed * l1h[j];
+        const float wu = un.w_signed - wl;
+#pragma unroll
+        for (int i = 0; i < NXT; ++i) {
+          const uint32_t lv = (i < 4) ? ((lb[j] >> (8 * i)) & 255u) : lb4[j];
+          const unsigned lc = lv - (unsigned)c_lo;
+          if (lc < (unsigned)cc) {
+            float4 v = Oc[lc * 32 + lane];
+            const float ur_ = wu * l1w[i], lr_ = wl * l1w[i];
+            v.x += wu - ur_; v.y += ur_; v.z += wl - lr_; v.w += lr_;
+            Oc[lc * 32 + lane] = v;
+          }
+        }
+      }
+    }
+
+    mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
+    const float* Sp = stages + slot * kStageFloats + un.xl;
+    for (int c = 0; c < cc; ++c) {
+      float v00 = Sp[0], v01 = Sp[1], v10 = Sp[kBoxW], v11 = Sp[kBoxW + 1];
+      Sp += 2 * kBoxW;
+      if (!a.src_scaled) { v00 *= kLog2e; v01 *= kLog2e; v10 *= kLog2e; v11 *= kLog2e; }
+      const float dv0 = v01 - v00, dv1 = v11 - v10;
+      const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
+      float2 CU2 = make_float2(0.f, 0.f), UR2 = CU2, CL2 = CU2, LR2 = CU2;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const float2 h0 = fma2(L1W[p], DV0, V0);
+        const float2 dd = sub2(fma2(L1W[p], DV1, V1), h0);
+        float2 t0 = make_float2(0.f, 0.f), t1 = t0;
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+          const float2 e = ex2_2(sub2(fma2(L1H[j], dd, h0), LW[j][p]));
+          t0 = add2(t0, e);
+          t1 = fma2(L1H[j], e, t1);
+        }
+        const float2 cu = sub2(t0, t1);
+        CU2 = add2(CU2, cu);
+        UR2 = fma2(L1W[p], cu, UR2);
+        CL2 = add2(CL2, t1);
+        LR2 = fma2(L1W[p], t1, LR2);
+      }
+      float CU = CU2.x + CU2.y, ur = UR2.x + UR2.y, CL = CL2.x + CL2.y, lr = LR2.x + LR2.y;
+      if (NX5) {
+        const float h0 = fmaf(l1w4, dv0, v00);
+        const float dd = fmaf(l1w4, dv1, v10) - h0;
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+          const float e = ex2_approx(fmaf(l1h[j], dd, h0) - lw4[j]);
+          t0 += e;
+          t1 = fmaf(l1h[j], e, t1);
+        }
+        const float cu = t0 - t1;
+        CU += cu; ur = fmaf(l1w4, cu, ur);
+        CL += t1; lr = fmaf(l1w4, t1, lr);
+      }
+      const float4 oh = Oc[c * 32 + lane];
+      const float uo = (CU - ur) * un.wsign - oh.x;
+      const float lo = (CL - lr) * un.wsign - oh.z;
+      ur = ur * un.wsign - oh.y;
+      lr = lr * un.wsign - oh.w;
+      float gu = __shfl_up_sync(0xffffffffu, ur, 1);
+      float gl = __shfl_up_sync(0xffffffffu, lr, 1);
+      if (lane == 0) { gu = 0.f; gl = 0.f; }
+      // vertical: add the lower-row half carried from the cell-row above; the finished row leaves the warp
+      const int cg = k * kKC + c;
+      const float up = uo + gu;
+      const float rowv = up + carry[cg * 32 + lane];
+      carry[cg * 32 + lane] = lo + gl;
+      if (first_partial) {
+        if (un.own) a.scrA[(((int64_t)un.b * a.n_seg + un.seg) * a.c_scr + (c_lo + c)) * a.gm.w + un.x] = up;
+      } else {
+        store_class<TO>(a, gd, un, outb, ucol, uptr, cg, g, rowv);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && q + kStages < un.n_loads) {  // the slot is free: every lane has read its corners
+      const int qn = q + kStages;
+      mbar_expect_tx(&bars[slot], kStageBytes);
+      load_4d(stages + slot * kStageFloats, map, &bars[slot], un.box_x, un.g0 + qn / un.n_ch,
+              un.c_beg + (qn % un.n_ch) * kKC, un.b);
+    }
+  }
+}
+
+constexpr size_t kOffOc = (size_t)kStages * kStageBytes;
+constexpr size_t kOffCarry = kOffOc + (size_t)kKC * 32 * 16;
+constexpr size_t kOffLw = kOffCarry + (size_t)kCG * 32 * 4;
+constexpr size_t kOffLab = kOffLw + (size_t)kMaxR * kStgW * 4;
+constexpr size_t kOffUcol = kOffLab + (size_t)kMaxR * kStgW;
+constexpr size_t kOffUptr = kOffUcol + (size_t)kUMax * 4;
+constexpr size_t kOffBars = kOffUptr + 144;
+constexpr size_t kSmem = kOffBars + (kStages + 1) * 8;
+static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffBars % 8 == 0, "shared memory carve-up alignment");
+
+template <typename TO>
+__global__ void __launch_bounds__(32) mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  float4* Oc = reinterpret_cast<float4*>(smem_raw + kOffOc);     // [kKC][32]
+  float* carry = reinterpret_cast<float*>(smem_raw + kOffCarry); // [kCG][32]
+  float* lw2s = reinterpret_cast<float*>(smem_raw + kOffLw);     // [kMaxR][kStgW]
+  uint8_t* labs = smem_raw + kOffLab;                            // [kMaxR][kStgW]
+  int* ucol = reinterpret_cast<int*>(smem_raw + kOffUcol);       // [kUMax]  u * h
+  int* uptr = reinterpret_cast<int*>(smem_raw + kOffUptr);       // [kCG + 1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);  // stage ring + staging barrier
+
+  const Geom& gm = a.gm;
+  const int lane = threadIdx.x;
+  const int b = blockIdx.z, grp = blockIdx.y;
+  const int strip = blockIdx.x % a.n_strips, seg = blockIdx.x / a.n_strips;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  const int h = gm.h, w = gm.w;
+  const int x0 = strip * kOwn;
+  const int x = x0 + lane - 1;
+  const bool own = lane >= 1 && x <= w - 1;
+  const int g0 = seg * a.seg_rows;
+  const int g1 = (g0 + a.seg_rows < h - 1) ? g0 + a.seg_rows : h - 1;
+  const bool last_seg = (g1 == h - 1);
+
+  if (d < 0 || d >= a.src.n_datasets) {
+    if (a.zero_invalid && grp == 0) {
+      TO* outb = (TO*)a.out_base[0] + (int64_t)b * a.out_image_stride[0];
+      for (int u = 0; u < a.out_channels[0]; ++u) zero_rows<TO>(a, outb, u, g0, g1, last_seg, x, own);
+    }
+    return;
+  }
+  const int C = a.src.C[d];
+  const int c_beg = grp * kCG;
+  if (c_beg >= C) return;
+  const int c_end = (c_beg + kCG < C) ? c_beg + kCG : C;
+  const GraphDev gd = a.g[d];
+  TO* outb = (TO*)a.out_base[d] + (int64_t)b * a.out_image_stride[d];
+  const mdseg_ohem_state* st = a.states + (a.src.seg_per_dataset ? d : 0);
+  const CUtensorMap* map = &maps.m[d];
+  const float wsel = (a.grad_out ? a.grad_out[a.src.seg_per_dataset ? d : 0] : 1.f) * a.grad_scale * st->inv_n_sel;
+
+  // horizontal geometry of this lane's cell
+  const bool cell_ok = (x >= 0) && (x <= w - 2);
+  int Xbeg = 0, Xend = 0;
+  if (cell_ok) cell_span(gm.xm, x, gm.W, Xbeg, Xend);
+  const int nx = Xend - Xbeg;
+  const unsigned cmask = __ballot_sync(0xffffffffu, cell_ok);
+  int Xw0 = 0;
+  if (cmask) Xw0 = __shfl_sync(0xffffffffu, Xbeg, __ffs(cmask) - 1);
+  float l1w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    int cell;
+    l1w[i] = 0.f;
+    if (i < nx) axis_cell(gm.xm, Xbeg + i, cell, l1w[i]);
+  }
+  const bool nx5 = __any_sync(0xffffffffu, nx > 4);
+
+  Unit un;
+  un.lane = lane; un.b = b; un.seg = seg; un.x = x; un.nx = nx; un.c_beg = c_beg; un.c_end = c_end;
+  un.n_ch = (c_end - c_beg + kKC - 1) / kKC;
+  un.g0 = g0; un.g1 = g1; un.own = own;
+  un.box_x = (x0 > 0 ? x0 - 1 : 0) & ~3;
+  un.xl = cell_ok ? x - un.box_x : 0;
+  un.n_loads = (g1 - g0) * un.n_ch;
+  un.Xa = Xw0 & ~15;
+  un.sx = cell_ok ? Xbeg - un.Xa : 0;
+  un.wst = (gm.W - un.Xa) < kStgW ? (gm.W - un.Xa) : kStgW;
+  un.w_signed = wsel; un.wsign = wsel < 0.f ? -1.f : 1.f;
+  un.p0 = 0; un.cached = false;
+
+  if (lane == 0) {
+    prefetch_map(map);
+    for (int s = 0; s <= kStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    issue_staging(a, un, g0, lw2s, labs, &bars[kStages]);
+    for (int qn = 0; qn < kStages && qn < un.n_loads; ++qn) {
+      mbar_expect_tx(&bars[qn], kStageBytes);
+      load_4d(stages + qn * kStageFloats, map, &bars[qn], un.box_x, g0 + qn / un.n_ch, c_beg + (qn % un.n_ch) * kKC,
+              b);
+    }
+  }
+  for (int cg = 0; cg < kCG; ++cg) carry[cg * 32 + lane] = 0.f;
+  // CSR slice of this class group: offsets per class + (u * h) per entry
+  if (gd.csr_ptr != nullptr) {
+    un.p0 = __ldg(gd.csr_ptr + c_beg);
+    const int n_e = __ldg(gd.csr_ptr + c_end) - un.p0;
+    for (int cg = lane; cg <= c_end - c_beg; cg += 32) uptr[cg] = __ldg(gd.csr_ptr + c_beg + cg) - un.p0;
+    un.cached = n_e <= kUMax;
+    if (un.cached)
+      for (int e = lane; e < n_e; e += 32) ucol[e] = __ldg(gd.csr_col + un.p0 + e) * h;
+  }
+  __syncwarp();
+
+  for (int g = g0; g < g1; ++g) {
+    int Ys, Ye;
+    cell_span(gm.ym, g, gm.H, Ys, Ye);
+    const int R = Ye - Ys;
+    float l1h[kMaxR];
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) {
+      int cell;
+      l1h[j] = 0.f;
+      if (j < R) axis_cell(gm.ym, Ys + j, cell, l1h[j]);
+    }
+    mbar_wait(&bars[kStages], (uint32_t)((g - g0) & 1));
+#define MDSEG_ROW(RT, N5) \
+  cell_row<TO, RT, N5>(a, map, gd, un, outb, g, R, l1w, l1h, stages, bars, Oc, carry, lw2s, labs, ucol, uptr)
+    if (R <= 4) {
+      if (nx5) MDSEG_ROW(4, true); else MDSEG_ROW(4, false);
+    } else {
+      if (nx5) MDSEG_ROW(5, true); else MDSEG_ROW(5, false);
+    }
+#undef MDSEG_ROW
+  }
+
+  // what is left in the carry is the lower-row half of row g1
+  for (int cg = 0; cg < c_end - c_beg; ++cg) {
+    const float v = carry[cg * 32 + lane];
+    if (last_seg) {
+      store_class<TO>(a, gd, un, outb, ucol, uptr, cg, h - 1, v);
+    } else if (own) {
+      a.scrB[(((int64_t)b * a.n_seg + (seg + 1)) * a.c_scr + (c_beg + cg)) * w + x] = v;
+    }
+  }
+  // unified classes no dataset class maps to: zero gradient
+  if (grp == 0 && gd.csr_ptr != nullptr && gd.csc_ptr != nullptr) {
+    for (int u0 = 0; u0 < a.out_channels[d]; u0 += 32) {
+      const int u = u0 + lane;
+      const bool empty = u < a.out_channels[d] && __ldg(gd.csc_ptr + u) == __ldg(gd.csc_ptr + u + 1);
+      unsigned m = __ballot_sync(0xffffffffu, empty);
+      while (m) {
+        const int uu = u0 + __ffs(m) - 1;
+        m &= m - 1;
+        zero_rows<TO>(a, outb, uu, g0, g1, last_seg, x, own);
+      }
+    }
+  }
+}
+
+// first row of every segment but the first: sum of the two halves, broadcast to the output channels
+template <typename TO>
+__global__ void __launch_bounds__(256) mds_bwd_fixup_kernel(const Args a) {
+  const int b = blockIdx.z, k = blockIdx.y + 1;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  if (d < 0 || d >= a.src.n_datasets) return;
+  const int C = a.src.C[d];
+  const int w = a.gm.w, h = a.gm.h, w4 = w / 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cls = idx / w4, x4 = idx - cls * w4;
+  if (cls >= C) return;
+  const int row = k * a.seg_rows;
+  const int64_t so = (((int64_t)b * a.n_seg + k) * a.c_scr + cls) * w + x4 * 4;
+  const float4 A = *reinterpret_cast<const float4*>(a.scrA + so);
+  const float4 B = *reinterpret_cast<const float4*>(a.scrB + so);
+  const float v[4] = {A.x + B.x, A.y + B.y, A.z + B.z, A.w + B.w};
+  const GraphDev gd = a.g[d];
+  TO* outb = (TO*)a.out_base[d] + (int64_t)b * a.out_image_stride[d];
+  if (gd.csr_ptr == nullptr) {
+    TO* o = outb + ((int64_t)cls * h + row) * w + x4 * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = from_f32<TO>(v[i]);
+    return;
+  }
+  const int e0 = __ldg(gd.csr_ptr + cls), e1 = __ldg(gd.csr_ptr + cls + 1);
+  for (int e = e0; e < e1; ++e) {
+    const int u = __ldg(gd.csr_col + e);
+    const float val = gd.csr_val ? __ldg(gd.csr_val + e) : 1.f;
+    TO* o = outb + ((int64_t)u * h + row) * w + x4 * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = from_f32<TO>(v[i] * val);
+  }
+}
+
+int pick_seg_rows(int h) { return h - 1 < 8 ? h - 1 : 8; }
+
+template <typename L>
+int launch_prep(const Args& a, int n_images, cudaStream_t s) {
+  const int64_t ppi = (int64_t)a.gm.H * a.gm.W;
+  int64_t bx = ceil_div64(ppi / 4, 256);
+  const int64_t want = ceil_div64((int64_t)sm_count() * 16, n_images);
+  if (bx > want) bx = want;
+  mds_bwd_prep_kernel<L><<<dim3((unsigned)bx, (unsigned)n_images), 256, 0, s>>>(a, ppi);
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+
+template <typename TO>
+int launch(int label_dtype, const Maps& maps, const Args& a, int n_images, int max_c, cudaStream_t s) {
+  int rc = 2;
+  switch (label_dtype) {
+    case MDSEG_U8: rc = launch_prep<uint8_t>(a, n_images, s); break;
+    case MDSEG_I32: rc = launch_prep<int32_t>(a, n_images, s); break;
+    case MDSEG_I64: rc = launch_prep<int64_t>(a, n_images, s); break;
+    default: set_error("mdseg_mds_bwd: unsupported label dtype %d", label_dtype);
+  }
+  if (rc) return rc;
+  auto k = mds_bwd_kernel<TO>;
+  MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+  dim3 grid((unsigned)(a.n_strips * a.n_seg), (unsigned)((max_c + kCG - 1) / kCG), (unsigned)n_images);
+  k<<<grid, 32, kSmem, s>>>(maps, a);
+  MDSEG_LAUNCH_OK();
+  if (a.n_seg > 1) {
+    dim3 g2((unsigned)(((int64_t)max_c * (a.gm.w / 4) + 255) / 256), (unsigned)(a.n_seg - 1), (unsigned)n_images);
+    mds_bwd_fixup_kernel<TO><<<g2, 256, 0, s>>>(a);
+    MDSEG_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int src_max_c(const mdseg_src_table* s) {
+  int m = 0;
+  for (int i = 0; i < s->n_datasets; ++i) m = s->C[i] > m ? s->C[i] : m;
+  return m;
+}
+
+}  // namespace
+}  // namespace mdseg
+
+namespace mdseg {
+namespace {
+Geom geom_of(int h, int w, int H, int W) {
+  Geom gm;
+  gm.ym.scale = axis_scale(h, H); gm.ym.n_in = h;
+  gm.xm.scale = axis_scale(w, W); gm.xm.n_in = w;
+  gm.h = h; gm.w = w; gm.H = H; gm.W = W;
+  return gm;
+}
+// the fused kernel covers fp32 sources, column-one-hot sparse graphs and up-sampling factors in [1, 5]
+bool fused_route(const mdseg_src_table* src, const mdseg_graph_table* graphs, const Geom& gm) {
+  for (int i = 0; i < src->n_datasets; ++i) {
+    const mdseg_sparse_graph& g = graphs->g[i];
+    if (g.dense || !g.col_onehot || !g.csr_ptr || !g.csc_ptr || g.C_ds != src->C[i]) return false;
+  }
+  if (gm.W % 16 != 0) return false;  // label rows are staged with 16-byte bulk copies
+  return tma::fast_geometry(*src, gm);
+}
+}  // namespace
+}  // namespace mdseg
+
+extern "C" size_t mdseg_mds_bwd_workspace_bytes(const mdseg_src_table* src, const mdseg_graph_table* graphs,
+                                                int n_images, int h, int w, int H, int W) {
+  using namespace mdseg;
+  if (!src || !graphs || src->n_datasets <= 0 || src->n_datasets > MDSEG_MAX_DATASETS ||
+      graphs->n_datasets != src->n_datasets || n_images <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0)
+    return 256;
+  const int c_max = src_max_c(src);
+  if (fused_route(src, graphs, geom_of(h, w, H, W))) {
+    const int sr = pick_seg_rows(h);
+    const int n_seg = (h - 1 + sr - 1) / sr;
+    return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W * 5 + 1024;
+  }
+  return 2 * (size_t)n_images * c_max * h * w * 4 + 256;  // generic route: two gradient planes
+}
+
+extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table* graphs, const int32_t* dataset_ids,
+                             const void* labels, int label_dtype, int n_images, int h, int w, int H, int W, int ignore,
+                             const float* loss_px, const float* lse_px, mdseg_ohem_state* states,
+                             const float* grad_out, float grad_scale, void* dx, int dx_dtype, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(src && graphs && src->n_datasets > 0 && src->n_datasets <= MDSEG_MAX_DATASETS &&
+                    graphs->n_datasets == src->n_datasets && graphs->C_uni > 0,
+                "mdseg_mds_bwd: bad source / graph table");
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0 && H > 0 && W > 0 && h <= 65535,
+                "mdseg_mds_bwd: bad shape");
+  if (n_images == 0) return 0;
+  MDSEG_REQUIRE(labels && loss_px && lse_px && states && dx && workspace, "mdseg_mds_bwd: null pointer");
+  MDSEG_REQUIRE(is_float_dtype(dx_dtype), "mdseg_mds_bwd: unsupported gradient dtype %d", dx_dtype);
+  const int c_max = src_max_c(src);
+  MDSEG_REQUIRE(workspace_bytes >= mdseg_mds_bwd_workspace_bytes(src, graphs, n_images, h, w, H, W),
+                "mdseg_mds_bwd: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t hw = (int64_t)h * w;
+  float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+
+  const Geom gm = geom_of(h, w, H, W);
+  const bool fused = fused_route(src, graphs, gm);
+
+  if (!fused) {
+    // generic route: adjoint of the upsample into two planes, then the projection adjoint
+    float* dyA = ws;
+    float* dyB = ws + (size_t)n_images * c_max * hw;
+    mdseg_src_table dA = *src, dB = *src;
+    dA.dtype = MDSEG_F32; dB.dtype = MDSEG_F32; dA.cmax = nullptr; dB.cmax = nullptr;
+    for (int i = 0; i < src->n_datasets; ++i) {
+      dA.base[i] = dyA; dB.base[i] = dyB;
+      dA.image_stride[i] = (long long)c_max * hw; dB.image_stride[i] = (long long)c_max * hw;
+      dA.C_alloc[i] = c_max; dB.C_alloc[i] = c_max;
+    }
+    if (int rc = mdseg_up_ce_bwd(src, dataset_ids, labels, label_dtype, n_images, h, w, H, W, ignore, loss_px, lse_px,
+                                 states, grad_out, grad_scale, &dA, &dB, stream))
+      return rc;
+    return mdseg_proj_bwd(dyA, dyB, c_max, graphs, dataset_ids, n_images, h, w, dx, dx_dtype, stream);
+  }
+
+  Args a;
+  a.src = *src; a.src_scaled = 0; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
+  a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
+  for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
+    a.out_base[i] = dx; a.out_image_stride[i] = (long long)graphs->C_uni * hw; a.out_channels[i] = graphs->C_uni;
+    a.g[i] = GraphDev{nullptr, nullptr, nullptr, nullptr};
+    if (i < src->n_datasets) {
+      const mdseg_sparse_graph& g = graphs->g[i];
+      a.g[i] = GraphDev{g.csr_ptr, g.csr_col, g.csr_val, g.csc_ptr};
+    }
+  }
+  a.zero_invalid = 1;
+  a.seg_rows = pick_seg_rows(h);
+  a.n_seg = (h - 1 + a.seg_rows - 1) / a.seg_rows;
+  a.n_strips = (w + kOwn - 1) / kOwn;
+  a.c_scr = c_max;
+  a.scrA = ws;
+  a.scrB = ws + (size_t)n_images * a.n_seg * c_max * w;
+  a.lw2 = a.scrB + (size_t)n_images * a.n_seg * c_max * w;
+  a.sel8 = reinterpret_cast<uint8_t*>(a.lw2 + (size_t)n_images * H * W);
+  tma::Maps maps;
+  if (int rc = tma::make_maps(a.src, gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
+  switch (dx_dtype) {
+    case MDSEG_F32: return launch<float>(label_dtype, maps, a, n_images, c_max, s);
+    case MDSEG_BF16: return launch<__nv_bfloat16>(label_dtype, maps, a, n_images, c_max, s);
+    case MDSEG_F16: return launch<__half>(label_dtype, maps, a, n_images, c_max, s);
+  }
+  return 2;
+}

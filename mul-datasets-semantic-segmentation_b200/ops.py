@@ -388,6 +388,18 @@ class _MdsProjOhemCE(torch.autograd.Function):
         scratch = torch.empty(1, dtype=torch.float32, device=dev)  # non-NULL cmax selects the TMA kernels
         src = _src_table([y.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False, c_alloc=cmax, cmax=scratch,
                          cmax_ready=True)
+        want_dg = any(ctx.needs_input_grad[6 + i] for i in range(n))
+        if not want_dg:
+            # one call: softmax recompute + adjoint of the upsample + broadcast through G^T (fused when it applies)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                nbytes = N.lib.mdseg_mds_bwd_workspace_bytes(C.byref(src), C.byref(tab), B, h, w, H, W)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                dx = torch.empty_like(x)
+                N.call("mdseg_mds_bwd", C.byref(src), C.byref(tab), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h,
+                       w, H, W, ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, _ptr(dx), _DT[x.dtype],
+                       _ptr(ws), nbytes, _stream())
+            return (dx, None, None, None, None, None, *([None] * n))
         dyA = torch.empty_like(y)
         dyB = torch.empty_like(y)
         dA = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
@@ -400,7 +412,7 @@ class _MdsProjOhemCE(torch.autograd.Function):
             N.call("mdseg_proj_bwd", _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dx),
                    _DT[x.dtype], _stream())
         dgs = [None] * n
-        if any(ctx.needs_input_grad[6 + i] for i in range(n)):
+        if want_dg:
             stride = cmax * Cu
             dG = torch.zeros(n, stride, dtype=torch.float32, device=dev)
             N.call("mdseg_proj_bwd_graph", _ptr(x), _DT[x.dtype], _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids),
