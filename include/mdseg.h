@@ -127,6 +127,11 @@ typedef struct mdseg_sparse_graph {
   int col_onehot;        /* every column has at most one entry (UOT / pretrain graphs,
                             ltbgnn_direct_learn.py:426-439,689-692) */
   int reserved;
+  /* optional (may be NULL): the CSR rows padded to a multiple of 4 entries by repeating the
+   * last entry of the row; csr4_ptr[n] is the row start in QUADS.  Lets mdseg_mds_bwd fetch four
+   * unified ids per shared-memory load when it broadcasts a dataset-class gradient. */
+  const int* csr4_ptr;   /* [C_ds + 1]  */
+  const int* csr4_col;   /* [4 * csr4_ptr[C_ds]] */
 } mdseg_sparse_graph;
 
 typedef struct mdseg_graph_table {

@@ -30,22 +30,24 @@ namespace {
 
 using namespace tma;
 
-constexpr int kKC = 16;                         // classes per TMA stage
+constexpr int kKC = 8;                          // classes per TMA stage
 constexpr int kBoxW = 36;                       // staged columns: <= 3 alignment + 33
 constexpr int kStages = 2;
 constexpr int kStageFloats = kKC * 2 * kBoxW;   // 1152
 constexpr int kStageBytes = kStageFloats * 4;   // 4608
-constexpr int kCG = 32;                         // classes per unit
+constexpr int kCG = 16;                         // classes per unit
 constexpr int kOwn = 31;                        // owned columns per strip
 constexpr int kStgW = 176;                      // staged label columns: <= 15 alignment + 32 cells x 5
 constexpr int kMaxR = 5;
-constexpr int kUMax = 384;                      // CSR entries of one class group cached in shared memory
+constexpr int kUQ = 120;                        // quads of padded CSR entries of one class group cached in shared memory
 
 struct GraphDev {
   const int* csr_ptr;  // NULL: identity (output channel = class)
   const int* csr_col;
   const float* csr_val;
   const int* csc_ptr;
+  const int* csr4_ptr;  // optional: rows padded to multiples of 4 entries (last entry repeated), in quads
+  const int* csr4_col;
 };
 
 struct Args {
@@ -78,6 +80,34 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// store v at base + off elements with exactly one IMAD.WIDE + one STG (the compiler's own 64-bit
+// address arithmetic for `base[off]` inside the broadcast loop costs five instructions per store)
+__device__ __forceinline__ void st_off(float* base, int off, float v) {
+  asm volatile("{ .reg .u64 a; mad.wide.s32 a, %1, 4, %0; st.global.f32 [a], %2; }" ::"l"(base), "r"(off), "f"(v)
+               : "memory");
+}
+__device__ __forceinline__ void st_off(__nv_bfloat16* base, int off, __nv_bfloat16 v) {
+  asm volatile("{ .reg .u64 a; mad.wide.s32 a, %1, 2, %0; st.global.b16 [a], %2; }" ::"l"(base), "r"(off),
+               "h"(*reinterpret_cast<unsigned short*>(&v))
+               : "memory");
+}
+__device__ __forceinline__ void st_off(__half* base, int off, __half v) {
+  asm volatile("{ .reg .u64 a; mad.wide.s32 a, %1, 2, %0; st.global.b16 [a], %2; }" ::"l"(base), "r"(off),
+               "h"(*reinterpret_cast<unsigned short*>(&v))
+               : "memory");
+}
+
+// e -= |w| where the pixel's class (fp16 pair `lab2`) equals the current class (`c2`): one packed compare, two
+// predicated adds.  e holds |w|*softmax, so e - |w|*[c == label] is |w| * d loss / d z.
+__device__ __forceinline__ void sub_onehot2(float2& e, uint32_t lab2, uint32_t c2, float nwabs) {
+  asm("{ .reg .pred p, q;\n"
+      "  setp.eq.f16x2 p|q, %2, %3;\n"
+      "  @p add.f32 %0, %0, %4;\n"
+      "  @q add.f32 %1, %1, %4; }"
+      : "+f"(e.x), "+f"(e.y)
+      : "r"(lab2), "r"(c2), "f"(nwabs));
 }
 
 // ---- pass 0: selection state of every label pixel in the form the main kernel consumes --------------------
@@ -129,44 +159,50 @@ __device__ __forceinline__ void zero_rows(const Args& a, TO* outb, int u, int r0
 }
 
 struct Unit {
-  int lane, b, seg, x, xl, sx, nx, c_beg, c_end, n_ch, g0, g1, box_x, n_loads, Xa, wst, p0;
+  int lane, b, seg, x, xl, sx, nx, c_beg, c_end, n_ch, g0, g1, box_x, n_loads, Xa, wst;
   bool own, cached;
   float w_signed, wsign;
 };
 
 // value v of class `cls` (group-relative index cg) at (row, x): broadcast to the output channels of the class
 template <typename TO>
-__device__ __forceinline__ void store_class(const Args& a, const GraphDev& gd, const Unit& un, TO* outb,
+__device__ __forceinline__ void store_class(const Args& a, const GraphDev& gd, const Unit& un, TO* outb, TO* orow,
                                             const int* ucol, const int* uptr, int cg, int row, float v) {
   const int w = a.gm.w;
   if (gd.csr_ptr == nullptr) {
     if (un.own) outb[((int64_t)(un.c_beg + cg) * a.gm.h + row) * w + un.x] = from_f32<TO>(v);
     return;
   }
-  const int e0 = uptr[cg], e1 = uptr[cg + 1];
-  if (un.cached && gd.csr_val == nullptr) {
+  if (un.cached) {
+    // padded quads of element offsets u*h*w: one LDS.128 per four channel stores, next quad in flight
     const TO tv = from_f32<TO>(v);
-    TO* o = outb + (int64_t)row * w + un.x;
-#pragma unroll 4
-    for (int e = e0; e < e1; ++e) {
-      const int uh = ucol[e];  // u * h
-      if (un.own) o[(int64_t)uh * w] = tv;
+    TO* o = orow;
+    const int4* U = reinterpret_cast<const int4*>(ucol);
+    int q = uptr[cg];
+    const int q1 = uptr[cg + 1];
+    if (q < q1) {
+      int4 cur = U[q];
+      for (; q < q1; ++q) {
+        const int4 nxt = U[q + 1];  // next quad in flight while this one is stored
+        if (un.own) {
+          st_off(o, cur.x, tv); st_off(o, cur.y, tv); st_off(o, cur.z, tv); st_off(o, cur.w, tv);
+        }
+        cur = nxt;
+      }
     }
   } else {
+    const int e0 = __ldg(gd.csr_ptr + un.c_beg + cg), e1 = __ldg(gd.csr_ptr + un.c_beg + cg + 1);
     for (int e = e0; e < e1; ++e) {
-      const int u = __ldg(gd.csr_col + un.p0 + e);
-      const float val = gd.csr_val ? __ldg(gd.csr_val + un.p0 + e) : 1.f;
+      const int u = __ldg(gd.csr_col + e);
+      const float val = gd.csr_val ? __ldg(gd.csr_val + e) : 1.f;
       if (un.own) outb[((int64_t)u * a.gm.h + row) * w + un.x] = from_f32<TO>(v * val);
     }
   }
 }
 
 // lane 0: queue the selection state (lw2 + class byte rows) of cell-row g into shared memory
-__device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int g, float* lw2s, uint8_t* labs,
+__device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int Ys, int R, float* lw2s, uint8_t* labs,
                                               uint64_t* sbar) {
-  int Ys, Ye;
-  cell_span(a.gm.ym, g, a.gm.H, Ys, Ye);
-  const int R = Ye - Ys;
   mbar_expect_tx(sbar, (uint32_t)(R * un.wst * 5));
   for (int j = 0; j < R; ++j) {
     const int64_t p = ((int64_t)un.b * a.gm.H + (Ys + j)) * a.gm.W + un.Xa;
@@ -178,38 +214,39 @@ __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int
 // One cell-row: all class chunks of the unit.  RT rows / 4 (+1 when NX5) columns are the compiled loop bounds.
 template <typename TO, int RT, bool NX5>
 __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, const GraphDev& gd, const Unit& un,
-                                         TO* outb, int g, int R, const float (&l1w)[5], const float (&l1h)[kMaxR],
-                                         float* stages, uint64_t* bars, float4* Oc, float* carry, float* lw2s,
+                                         TO* outb, int g, int R, int Ys_next, int R_next, const float (&l1w)[5],
+                                         const float (&l1h)[kMaxR],
+                                         float* stages, uint64_t* bars, float* carry, float* lw2s,
                                          uint8_t* labs, const int* ucol, const int* uptr) {
   const int lane = un.lane;
   const float kInf = __int_as_float(0x7f800000);
-  constexpr int NXT = NX5 ? 5 : 4;
   // per-pixel exponent offsets and class bytes of this lane's cell, from the staged rows
   float2 LW[RT][2];
   float lw4[RT];
-  uint32_t lb[RT], lb4[RT];
+  uint32_t LH[RT][2], lh4[RT];  // class ids as fp16 pairs (255.0 = no gradient), compared two at a time
 #pragma unroll
   for (int j = 0; j < RT; ++j) {
     float t[5];
-    uint32_t bytes = 0xffffffffu, b4 = 255u;
+    uint32_t hv[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       t[i] = kInf;
+      hv[i] = 255u;
       if (j < R && i < un.nx) {
         t[i] = lw2s[j * kStgW + un.sx + i];
-        const uint32_t v = labs[j * kStgW + un.sx + i];
-        if (i < 4) bytes = (bytes & ~(255u << (8 * i))) | (v << (8 * i));
-        else b4 = v;
+        hv[i] = labs[j * kStgW + un.sx + i];
       }
+      hv[i] = (uint32_t)__half_as_ushort(__ushort2half_rn((unsigned short)hv[i]));
     }
     LW[j][0] = make_float2(t[0], t[1]);
     LW[j][1] = make_float2(t[2], t[3]);
     lw4[j] = t[4];
-    lb[j] = bytes;
-    lb4[j] = b4;
+    LH[j][0] = hv[0] | (hv[1] << 16);
+    LH[j][1] = hv[2] | (hv[3] << 16);
+    lh4[j] = hv[4] | (0x5bf8u << 16);  // high half 255.0: never a class
   }
   __syncwarp();
-  if (lane == 0 && g + 1 < un.g1) issue_staging(a, un, g + 1, lw2s, labs, &bars[kStages]);
+  if (lane == 0 && g + 1 < un.g1) issue_staging(a, un, Ys_next, R_next, lw2s, labs, &bars[kStages]);
 
   float2 L1H[RT];
 #pragma unroll
@@ -217,33 +254,16 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
   const float2 L1W[2] = {make_float2(l1w[0], l1w[1]), make_float2(l1w[2], l1w[3])};
   const float l1w4 = l1w[4];
   const bool first_partial = (g == un.g0) && (un.g0 > 0);
+  // this lane's element of row g in channel 0; opaque so that the broadcast loop keeps it in a register pair
+  TO* orow = outb + (int64_t)g * a.gm.w + un.x;
+  asm volatile("" : "+l"(orow));
+  const float nwabs = -fabsf(un.w_signed);
 
   for (int k = 0; k < un.n_ch; ++k) {
     const int q = (g - un.g0) * un.n_ch + k;
     const int slot = q % kStages;
     const int c_lo = un.c_beg + k * kKC;
     const int cc = (un.c_end - c_lo) < kKC ? (un.c_end - c_lo) : kKC;
-
-    // -w*[c == label] per corner, accumulated first into lane-private slots {own-up, right-up, own-low, right-low}
-    for (int c = 0; c < cc; ++c) Oc[c * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      if (j < R) {
-        const float wl = un.w_signed * l1h[j];
-        const float wu = un.w_signed - wl;
-#pragma unroll
-        for (int i = 0; i < NXT; ++i) {
-          const uint32_t lv = (i < 4) ? ((lb[j] >> (8 * i)) & 255u) : lb4[j];
-          const unsigned lc = lv - (unsigned)c_lo;
-          if (lc < (unsigned)cc) {
-            float4 v = Oc[lc * 32 + lane];
-            const float ur_ = wu * l1w[i], lr_ = wl * l1w[i];
-            v.x += wu - ur_; v.y += ur_; v.z += wl - lr_; v.w += lr_;
-            Oc[lc * 32 + lane] = v;
-          }
-        }
-      }
-    }
 
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
@@ -254,6 +274,8 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       const float dv0 = v01 - v00, dv1 = v11 - v10;
       const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
       float2 CU2 = make_float2(0.f, 0.f), UR2 = CU2, CL2 = CU2, LR2 = CU2;
+      const uint32_t ch = (uint32_t)__half_as_ushort(__int2half_rn(c_lo + c));
+      const uint32_t c2 = ch | (ch << 16);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const float2 h0 = fma2(L1W[p], DV0, V0);
@@ -261,7 +283,8 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
         float2 t0 = make_float2(0.f, 0.f), t1 = t0;
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
-          const float2 e = ex2_2(sub2(fma2(L1H[j], dd, h0), LW[j][p]));
+          float2 e = ex2_2(sub2(fma2(L1H[j], dd, h0), LW[j][p]));
+          sub_onehot2(e, LH[j][p], c2, nwabs);
           t0 = add2(t0, e);
           t1 = fma2(L1H[j], e, t1);
         }
@@ -278,19 +301,19 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
         float t0 = 0.f, t1 = 0.f;
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
-          const float e = ex2_approx(fmaf(l1h[j], dd, h0) - lw4[j]);
-          t0 += e;
-          t1 = fmaf(l1h[j], e, t1);
+          float2 e = make_float2(ex2_approx(fmaf(l1h[j], dd, h0) - lw4[j]), 0.f);
+          sub_onehot2(e, lh4[j], c2, nwabs);
+          t0 += e.x;
+          t1 = fmaf(l1h[j], e.x, t1);
         }
         const float cu = t0 - t1;
         CU += cu; ur = fmaf(l1w4, cu, ur);
         CL += t1; lr = fmaf(l1w4, t1, lr);
       }
-      const float4 oh = Oc[c * 32 + lane];
-      const float uo = (CU - ur) * un.wsign - oh.x;
-      const float lo = (CL - lr) * un.wsign - oh.z;
-      ur = ur * un.wsign - oh.y;
-      lr = lr * un.wsign - oh.w;
+      const float uo = (CU - ur) * un.wsign;
+      const float lo = (CL - lr) * un.wsign;
+      ur *= un.wsign;
+      lr *= un.wsign;
       float gu = __shfl_up_sync(0xffffffffu, ur, 1);
       float gl = __shfl_up_sync(0xffffffffu, lr, 1);
       if (lane == 0) { gu = 0.f; gl = 0.f; }
@@ -302,7 +325,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       if (first_partial) {
         if (un.own) a.scrA[(((int64_t)un.b * a.n_seg + un.seg) * a.c_scr + (c_lo + c)) * a.gm.w + un.x] = up;
       } else {
-        store_class<TO>(a, gd, un, outb, ucol, uptr, cg, g, rowv);
+        store_class<TO>(a, gd, un, outb, orow, ucol, uptr, cg, g, rowv);
       }
     }
     __syncwarp();
@@ -315,25 +338,25 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
   }
 }
 
-constexpr size_t kOffOc = (size_t)kStages * kStageBytes;
-constexpr size_t kOffCarry = kOffOc + (size_t)kKC * 32 * 16;
+constexpr size_t kOffCarry = (size_t)kStages * kStageBytes;
 constexpr size_t kOffLw = kOffCarry + (size_t)kCG * 32 * 4;
 constexpr size_t kOffLab = kOffLw + (size_t)kMaxR * kStgW * 4;
 constexpr size_t kOffUcol = kOffLab + (size_t)kMaxR * kStgW;
-constexpr size_t kOffUptr = kOffUcol + (size_t)kUMax * 4;
+constexpr size_t kOffUptr = kOffUcol + (size_t)(kUQ + 1) * 16;
 constexpr size_t kOffBars = kOffUptr + 144;
 constexpr size_t kSmem = kOffBars + (kStages + 1) * 8;
-static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffBars % 8 == 0, "shared memory carve-up alignment");
+static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffUcol % 16 == 0 && kOffBars % 8 == 0,
+              "shared memory carve-up alignment");
+static_assert(kSmem <= 13568, "16 resident warps per SM need <= 13568 bytes of shared memory each");
 
 template <typename TO>
-__global__ void __launch_bounds__(32) mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a) {
+__global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
-  float4* Oc = reinterpret_cast<float4*>(smem_raw + kOffOc);     // [kKC][32]
   float* carry = reinterpret_cast<float*>(smem_raw + kOffCarry); // [kCG][32]
   float* lw2s = reinterpret_cast<float*>(smem_raw + kOffLw);     // [kMaxR][kStgW]
   uint8_t* labs = smem_raw + kOffLab;                            // [kMaxR][kStgW]
-  int* ucol = reinterpret_cast<int*>(smem_raw + kOffUcol);       // [kUMax]  u * h
+  int* ucol = reinterpret_cast<int*>(smem_raw + kOffUcol);       // [(kUQ + 1) * 4]  u * h * w
   int* uptr = reinterpret_cast<int*>(smem_raw + kOffUptr);       // [kCG + 1]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);  // stage ring + staging barrier
 
@@ -395,13 +418,17 @@ __global__ void __launch_bounds__(32) mds_bwd_kernel(const __grid_constant__ Map
   un.sx = cell_ok ? Xbeg - un.Xa : 0;
   un.wst = (gm.W - un.Xa) < kStgW ? (gm.W - un.Xa) : kStgW;
   un.w_signed = wsel; un.wsign = wsel < 0.f ? -1.f : 1.f;
-  un.p0 = 0; un.cached = false;
+  un.cached = false;
 
   if (lane == 0) {
     prefetch_map(map);
     for (int s = 0; s <= kStages; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
-    issue_staging(a, un, g0, lw2s, labs, &bars[kStages]);
+    {
+      int Ys0, Ye0;
+      cell_span(gm.ym, g0, gm.H, Ys0, Ye0);
+      issue_staging(a, un, Ys0, Ye0 - Ys0, lw2s, labs, &bars[kStages]);
+    }
     for (int qn = 0; qn < kStages && qn < un.n_loads; ++qn) {
       mbar_expect_tx(&bars[qn], kStageBytes);
       load_4d(stages + qn * kStageFloats, map, &bars[qn], un.box_x, g0 + qn / un.n_ch, c_beg + (qn % un.n_ch) * kKC,
@@ -409,20 +436,26 @@ __global__ void __launch_bounds__(32) mds_bwd_kernel(const __grid_constant__ Map
     }
   }
   for (int cg = 0; cg < kCG; ++cg) carry[cg * 32 + lane] = 0.f;
-  // CSR slice of this class group: offsets per class + (u * h) per entry
-  if (gd.csr_ptr != nullptr) {
-    un.p0 = __ldg(gd.csr_ptr + c_beg);
-    const int n_e = __ldg(gd.csr_ptr + c_end) - un.p0;
-    for (int cg = lane; cg <= c_end - c_beg; cg += 32) uptr[cg] = __ldg(gd.csr_ptr + c_beg + cg) - un.p0;
-    un.cached = n_e <= kUMax;
-    if (un.cached)
-      for (int e = lane; e < n_e; e += 32) ucol[e] = __ldg(gd.csr_col + un.p0 + e) * h;
+  // padded CSR slice of this class group: quad offsets per class + element offsets u*h*w per entry
+  if (gd.csr_ptr != nullptr && gd.csr4_ptr != nullptr && gd.csr_val == nullptr &&
+      (int64_t)a.out_channels[d] * h * w < 0x7fffffffLL) {
+    const int q_beg = __ldg(gd.csr4_ptr + c_beg);
+    const int n_q = __ldg(gd.csr4_ptr + c_end) - q_beg;
+    if (n_q <= kUQ) {
+      un.cached = true;
+      for (int cg = lane; cg <= c_end - c_beg; cg += 32) uptr[cg] = __ldg(gd.csr4_ptr + c_beg + cg) - q_beg;
+      for (int e = lane; e < n_q * 4; e += 32) ucol[e] = __ldg(gd.csr4_col + q_beg * 4 + e) * (h * w);
+      if (lane < 4) ucol[n_q * 4 + lane] = 0;
+    }
   }
   __syncwarp();
 
+  // label-row range of every cell-row of the segment: lane t holds the first label row of cell-row g0 + t
+  int ys_tab = gm.H;
+  if (g0 + lane < h - 1) ys_tab = first_dst_ge(gm.ym, g0 + lane, gm.H);
   for (int g = g0; g < g1; ++g) {
-    int Ys, Ye;
-    cell_span(gm.ym, g, gm.H, Ys, Ye);
+    const int Ys = __shfl_sync(0xffffffffu, ys_tab, g - g0);
+    const int Ye = __shfl_sync(0xffffffffu, ys_tab, g - g0 + 1);
     const int R = Ye - Ys;
     float l1h[kMaxR];
 #pragma unroll
@@ -431,9 +464,10 @@ __global__ void __launch_bounds__(32) mds_bwd_kernel(const __grid_constant__ Map
       l1h[j] = 0.f;
       if (j < R) axis_cell(gm.ym, Ys + j, cell, l1h[j]);
     }
+    const int Rn = __shfl_sync(0xffffffffu, ys_tab, (g - g0 + 2) & 31) - Ye;  // rows of the next cell-row
     mbar_wait(&bars[kStages], (uint32_t)((g - g0) & 1));
 #define MDSEG_ROW(RT, N5) \
-  cell_row<TO, RT, N5>(a, map, gd, un, outb, g, R, l1w, l1h, stages, bars, Oc, carry, lw2s, labs, ucol, uptr)
+  cell_row<TO, RT, N5>(a, map, gd, un, outb, g, R, Ye, Rn, l1w, l1h, stages, bars, carry, lw2s, labs, ucol, uptr)
     if (R <= 4) {
       if (nx5) MDSEG_ROW(4, true); else MDSEG_ROW(4, false);
     } else {
@@ -443,10 +477,12 @@ __global__ void __launch_bounds__(32) mds_bwd_kernel(const __grid_constant__ Map
   }
 
   // what is left in the carry is the lower-row half of row g1
+  TO* olast = outb + (int64_t)(h - 1) * w + x;
+  asm volatile("" : "+l"(olast));
   for (int cg = 0; cg < c_end - c_beg; ++cg) {
     const float v = carry[cg * 32 + lane];
     if (last_seg) {
-      store_class<TO>(a, gd, un, outb, ucol, uptr, cg, h - 1, v);
+      store_class<TO>(a, gd, un, outb, olast, ucol, uptr, cg, h - 1, v);
     } else if (own) {
       a.scrB[(((int64_t)b * a.n_seg + (seg + 1)) * a.c_scr + (c_beg + cg)) * w + x] = v;
     }
@@ -627,10 +663,10 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
   a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
   for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
     a.out_base[i] = dx; a.out_image_stride[i] = (long long)graphs->C_uni * hw; a.out_channels[i] = graphs->C_uni;
-    a.g[i] = GraphDev{nullptr, nullptr, nullptr, nullptr};
+    a.g[i] = GraphDev{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (i < src->n_datasets) {
       const mdseg_sparse_graph& g = graphs->g[i];
-      a.g[i] = GraphDev{g.csr_ptr, g.csr_col, g.csr_val, g.csc_ptr};
+      a.g[i] = GraphDev{g.csr_ptr, g.csr_col, g.csr_val, g.csc_ptr, g.csr4_ptr, g.csr4_col};
     }
   }
   a.zero_invalid = 1;

@@ -46,6 +46,7 @@ class SparseGraph(C.Structure):
         ("csc_ptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_val", C.c_void_p),
         ("dense", C.c_void_p),
         ("C_ds", C.c_int), ("nnz", C.c_int), ("col_onehot", C.c_int), ("reserved", C.c_int),
+        ("csr4_ptr", C.c_void_p), ("csr4_col", C.c_void_p),
     ]
 
 

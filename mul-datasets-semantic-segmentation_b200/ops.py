@@ -255,6 +255,19 @@ class BipartiteGraphs:
             ent["csr_val"] = None if all_ones else t(vals, np.float32)
             ent["csc_val"] = None if all_ones else t(vals[order], np.float32)
             ent["col_onehot"] = int(np.all(np.diff(csc_ptr) <= 1))
+            # rows padded to quads (last entry repeated) for the fused backward's channel broadcast
+            nq = (np.diff(csr_ptr) + 3) // 4
+            csr4_ptr = np.zeros(m.shape[0] + 1, dtype=np.int32)
+            np.cumsum(nq, out=csr4_ptr[1:])
+            csr4_col = np.zeros(4 * int(csr4_ptr[-1]), dtype=np.int32)
+            for r in range(m.shape[0]):
+                seg = cols[csr_ptr[r]:csr_ptr[r + 1]]
+                if len(seg):
+                    dst = csr4_col[4 * csr4_ptr[r]:4 * csr4_ptr[r + 1]]
+                    dst[:len(seg)] = seg
+                    dst[len(seg):] = seg[-1]
+            ent["csr4_ptr"] = t(csr4_ptr, np.int32)
+            ent["csr4_col"] = t(csr4_col, np.int32) if csr4_col.size else torch.zeros(4, dtype=torch.int32, device=dev)
         self._cache[i] = ent
         return ent
 
@@ -284,6 +297,7 @@ class BipartiteGraphs:
                 sg.csr_val = _ptr(e["csr_val"])
                 sg.csc_val = _ptr(e["csc_val"])
                 sg.col_onehot = e["col_onehot"]
+                sg.csr4_ptr, sg.csr4_col = e["csr4_ptr"].data_ptr(), e["csr4_col"].data_ptr()
                 keep.append(e)
         tab.C_uni = c_uni
         return tab, keep
