@@ -259,6 +259,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
   asm volatile("" : "+l"(orow));
   const float nwabs = -fabsf(un.w_signed);
 
+#pragma unroll 1
   for (int k = 0; k < un.n_ch; ++k) {
     const int q = (g - un.g0) * un.n_ch + k;
     const int slot = q % kStages;
@@ -267,6 +268,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
 
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
+#pragma unroll 1
     for (int c = 0; c < cc; ++c) {
       float v00 = Sp[0], v01 = Sp[1], v10 = Sp[kBoxW], v11 = Sp[kBoxW + 1];
       Sp += 2 * kBoxW;

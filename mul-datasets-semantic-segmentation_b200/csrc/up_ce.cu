@@ -658,6 +658,10 @@ extern "C" int mdseg_up_ce_fwd(const mdseg_src_table* src, const int32_t* datase
   a.cc_max = 0; a.fwp = 0;
   cudaStream_t s = (cudaStream_t)stream;
   {
+    const int rc = up_ce_fwd_warp(a, label_dtype, n_images, s);  // + uint8 labels, W % 16 == 0, cmax ready
+    if (rc >= 0) return rc;
+  }
+  {
     const int rc = up_ce_fwd_tma(a, label_dtype, n_images, s);  // fp32, w % 4 == 0, factor <= 5, cmax workspace
     if (rc >= 0) return rc;
   }

@@ -65,6 +65,7 @@ struct BwdArgs {
 
 // TMA-pipelined fast path (up_ce_tma.cu).  Return 0 = launched, -1 = not applicable
 // (caller falls back to the generic kernel), > 0 = error (set_error called).
+int up_ce_fwd_warp(const FwdArgs& a, int label_dtype, int n_images, cudaStream_t s);  // up_ce_warp.cu (uint8 labels)
 int up_ce_fwd_tma(const FwdArgs& a, int label_dtype, int n_images, cudaStream_t s);
 int up_ce_bwd_tma(const BwdArgs& a, int label_dtype, int n_images, cudaStream_t s);
 

@@ -43,6 +43,23 @@ def _labels(lb):
     return lb.contiguous()
 
 
+_IDENTITY_LUT = {}
+
+
+def _compact_labels(labels, c_max, ignore):
+    """int labels -> uint8 once (the kernels stage label rows as bytes; 8x less label traffic in every later
+    pass).  Values outside [0, 255] become a byte that is >= c_max and != ignore, so they are still flagged."""
+    if labels.dtype == torch.uint8:
+        return labels
+    oob = 254 if ignore != 254 else 253
+    if c_max > oob or not 0 <= ignore <= 255:
+        return labels
+    key = labels.device
+    if key not in _IDENTITY_LUT:
+        _IDENTITY_LUT[key] = torch.arange(256, dtype=torch.uint8, device=labels.device)
+    return lut_remap(labels, _IDENTITY_LUT[key], out_dtype=torch.uint8, oob=oob)
+
+
 # ---- lazily checked device-side data errors -----------------------------------
 _err_flags = {}
 
@@ -364,6 +381,7 @@ class _MdsProjOhemCE(torch.autograd.Function):
             raise ValueError("labels must be [B, H, W]")
         H, W = labels.shape[1:]
         dev = x.device
+        labels = _compact_labels(labels, max(g.shape[0] for g in graphs), ignore)
         tab, keep = cache.table(list(graphs))
         if tab.C_uni != Cu:
             raise ValueError(f"graphs have C_uni={tab.C_uni}, logits have {Cu}")
