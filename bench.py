@@ -157,7 +157,8 @@ class Clocks(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL = {"mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
+KERNELS_PER_CALL = {"mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
+                    "mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
                     "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
                     "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 2, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
 
@@ -192,33 +193,30 @@ def run_ours(args, rank, world, local_rank):
     px = B * H * W
     lab_dt = torch.int64 if args.label_dtype == "int64" else torch.uint8
     graphs = [g.to(dev) for g in bt["graphs"]]
-    luts = [torch.from_numpy(l).to(dev) for l in bt["luts"]]
+    luts = torch.from_numpy(np.stack(bt["luts"])).to(dev)  # [n_datasets, 256]
     ids_t = torch.tensor(ids, dtype=torch.int32, device=dev)
     slices = dataset_slices(ids)
     thresh = ops.neg_log(0.4)
     x = bt["x"].requires_grad_(True)
-    labels = torch.empty(B, H, W, dtype=lab_dt, device=dev)
     offs = np.cumsum([0] + [c * c for c in n_cats])
     hist_flat = torch.zeros(int(offs[-1]), dtype=torch.int64, device=dev)
     hists = [hist_flat[offs[d]:offs[d + 1]].view(n_cats[d], n_cats[d]) for d in range(len(n_cats))]
     out = {}
 
     def step(raw, xin, pred):
-        # a1: dataset lb_map LUT (lib/base_dataset.py:81-82), one table per dataset
-        for d, s, e in slices:
-            labels[s:e] = ops.lut_remap(raw[s:e], luts[d], out_dtype=lab_dt)
+        # a1: dataset lb_map LUT (lib/base_dataset.py:81-82), one table per dataset, one launch for the batch
+        labels = ops.lut_remap_images(raw, luts, ids_t, out_dtype=lab_dt)
         # a5-a9: fused projection + upsample + OhemCE fwd, selection, bwd
         xin.grad = None
         loss = ops.mds_proj_ohem_ce(xin, labels, ids_t, graphs, thresh)
         loss.backward()
-        # a12/a13: confusion matrices + mIoU
+        # a12/a13: confusion matrices of every dataset (one launch) + mIoU
         hist_flat.zero_()
-        for d, s, e in slices:
-            ops.confusion(labels[s:e], pred[s:e], n_cats[d], hist=hists[d])
+        ops.confusion_images(labels, pred, ids_t, n_cats, hist=hist_flat)
         if world > 1:
             dist.all_reduce(hist_flat)  # one int64 all-reduce for all datasets (evaluate.py:187-188)
-        mious = [ops.miou(hists[d])[1] for d, _, _ in slices]
-        out["loss"], out["miou"] = loss.detach(), torch.stack(mious)
+        _, mious = ops.miou_images(hist_flat, n_cats)
+        out["loss"], out["miou"] = loss.detach(), mious
 
     def barrier():
         if world > 1:
@@ -259,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
     d_x = torch.empty_like(bt["x"].detach()).requires_grad_(True)
     d_raw, d_pred = torch.empty_like(bt["raw"]), torch.empty_like(bt["pred"])
     h2d = h_x.numel() * h_x.element_size() + h_raw.numel() + h_pred.numel() * 8
-    d2h = 4 + 4 * len(slices)
+    d2h = 4 + 4 * len(n_cats)
 
     def e2e_step():
         with torch.no_grad():
@@ -317,6 +315,8 @@ def run_ours(args, rank, world, local_rank):
             "mdseg_mds_bwd": cbar * 4 / 16 + L + 8 + cu * e / 16,
             "mdseg_lut_remap": 1 + L,
             "mdseg_confusion": L + 8,
+            "mdseg_lut_remap_images": 1 + L,
+            "mdseg_confusion_images": L + 8,
         }
         for name, evs in per_call_ms.items():
             calls_per_step = len(evs) / 5

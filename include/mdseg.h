@@ -166,6 +166,29 @@ int mdseg_confusion(const void* label, int label_dtype, const void* pred,
                     int Ca, int Cb, int ignore, int64_t n, int32_t* err_flag,
                     void* stream);
 
+/* ---- a1 + a12 for a whole multi-dataset batch in one launch each -----------------------------
+ * The trainers' batch holds images of several datasets (tools/train_ltbgnn_all_datasets_snp.py:708-750,
+ * lib/MultiSetReader.py:26-34); the reference remaps / evaluates them dataset by dataset.  Here image
+ * b uses table / class count / histogram of dataset dataset_ids[b] (NULL: dataset 0). */
+typedef struct mdseg_hist_table {
+  int n_datasets;
+  int C[MDSEG_MAX_DATASETS];             /* classes of dataset d: its histogram is C[d] x C[d] */
+  long long offset[MDSEG_MAX_DATASETS];  /* element offset of that histogram inside `hist`      */
+} mdseg_hist_table;
+/* out[b, p] = luts[lut_ids[b]][in[b, p]]; luts: device uint8 [n_luts][256] */
+int mdseg_lut_remap_images(const void* in, int in_dtype, void* out, int out_dtype, const uint8_t* luts, int n_luts,
+                           const int32_t* lut_ids, int oob, int n_images, int64_t px_per_image, int32_t* err_flag,
+                           void* stream);
+/* hist_d[l*C_d + q] += 1 over the images of dataset d, for every dataset; luts (optional, device
+ * uint8 [n_datasets][256]) are applied to the labels first.  Images are px_per_image % 16 == 0. */
+int mdseg_confusion_images(const void* label, int label_dtype, const void* pred, int pred_dtype,
+                           const uint8_t* luts, const int32_t* dataset_ids, int n_images, int64_t px_per_image,
+                           int64_t* hist, const mdseg_hist_table* tab /*host*/, int ignore, int32_t* err_flag,
+                           void* stream);
+/* iou[d*iou_stride + c], miou[d] for every dataset (evaluate.py:94-98) */
+int mdseg_miou_images(const int64_t* hist, const mdseg_hist_table* tab /*host*/, float* iou, int iou_stride,
+                      float* miou, void* stream);
+
 /* ---- a13: IoU from the histogram (device, no sync) ------------------------
  * iou[c] = h[c,c] / (Σ_r h[r,c] + Σ_q h[c,q] - h[c,c]) (NaN when 0/0) and
  * miou = nanmean(iou).  evaluate.py:94-98. */

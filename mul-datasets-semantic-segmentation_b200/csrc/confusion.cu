@@ -131,6 +131,138 @@ confusion_kernel(const L* __restrict__ label, const P* __restrict__ pred, const 
   }
 }
 
+// ---- all datasets of a batch in one launch --------------------------------------------------------------
+// blockIdx.y = image b; d = dataset_ids[b] selects the LUT (luts + 256*d), the class count C[d] and the
+// square histogram hist + offset[d].  Shared-memory privatisation is decided per CTA from C[d].
+template <typename L, typename P>
+__global__ void __launch_bounds__(256)
+confusion_images_kernel(const L* __restrict__ label, const P* __restrict__ pred, const uint8_t* __restrict__ luts,
+                        const int32_t* __restrict__ dataset_ids, int64_t px_per_image,
+                        unsigned long long* __restrict__ hist, const mdseg_hist_table tab, int ignore,
+                        int* err_flag, int smem_words) {
+  extern __shared__ unsigned sh_hist[];
+  __shared__ uint8_t s_lut[256];
+  const int b = blockIdx.y;
+  const int d = dataset_ids ? dataset_ids[b] : 0;
+  if (d < 0 || d >= tab.n_datasets) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err_flag, MDSEG_ERR_DATASET_ID);
+    return;
+  }
+  const int C = tab.C[d];
+  const int bins = C * C;
+  unsigned long long* h = hist + tab.offset[d];
+  const bool has_lut = luts != nullptr;
+  if (has_lut) s_lut[threadIdx.x] = luts[(int64_t)d * 256 + threadIdx.x];
+  const bool use_smem = bins <= smem_words;
+  int replicas = 1;
+  if (use_smem) {
+    replicas = smem_words / bins;
+    if (replicas > 8) replicas = 8;
+    for (int i = threadIdx.x; i < bins * replicas; i += blockDim.x) sh_hist[i] = 0u;
+  }
+  __syncthreads();
+  unsigned* my = sh_hist + (use_smem ? ((threadIdx.x >> 5) % replicas) * bins : 0);
+  label += (int64_t)b * px_per_image;
+  pred += (int64_t)b * px_per_image;
+
+  int err = 0;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nvec = px_per_image / kPx;  // the host guarantees 16-byte aligned image slices
+  for (int64_t v = gtid; v < nvec; v += gstride) {
+    int l[kPx], p[kPx];
+    Load8<L>::load(label + v * kPx, l);
+    Load8<P>::load(pred + v * kPx, p);
+    int prev = -1;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kPx; ++i) {
+      int key = make_key(l[i], p[i], s_lut, has_lut, C, C, ignore, err);
+      if (key == prev) {
+        ++cnt;
+      } else {
+        if (prev >= 0) { if (use_smem) atomicAdd(my + prev, cnt); else atomicAdd(h + prev, (unsigned long long)cnt); }
+        prev = key;
+        cnt = 1;
+      }
+    }
+    if (prev >= 0) { if (use_smem) atomicAdd(my + prev, cnt); else atomicAdd(h + prev, (unsigned long long)cnt); }
+  }
+  if (err) atomicOr(err_flag, err);
+  if (use_smem) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < bins; k += blockDim.x) {
+      unsigned long long sum = 0;
+      for (int r = 0; r < replicas; ++r) sum += sh_hist[r * bins + k];
+      if (sum) atomicAdd(h + k, sum);
+    }
+  }
+}
+
+// iou / mIoU of every dataset: one CTA per dataset (see miou_kernel)
+__global__ void miou_images_kernel(const long long* __restrict__ hist, const mdseg_hist_table tab,
+                                   float* __restrict__ iou, int iou_stride, float* __restrict__ miou) {
+  const int d = blockIdx.x;
+  const int C = tab.C[d];
+  const long long* h = hist + tab.offset[d];
+  float* io = iou + (int64_t)d * iou_stride;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long row = 0, col = 0;
+    for (int j = 0; j < C; ++j) { row += h[(int64_t)c * C + j]; col += h[(int64_t)j * C + c]; }
+    const long long dg = h[(int64_t)c * C + c];
+    io[c] = (float)((double)dg / (double)(col + row - dg));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    int cnt = 0;
+    for (int c = 0; c < C; ++c) {
+      const float v = io[c];
+      if (v == v) { sum += (double)v; ++cnt; }
+    }
+    miou[d] = cnt ? (float)(sum / cnt) : __int_as_float(0x7fc00000);
+  }
+}
+
+template <typename L, typename P>
+int launch_images(const void* label, const void* pred, const uint8_t* luts, const int32_t* ids, int n_images,
+                  int64_t ppi, int64_t* hist, const mdseg_hist_table& tab, int ignore, int32_t* err_flag,
+                  cudaStream_t st) {
+  int cmax = 0;
+  for (int i = 0; i < tab.n_datasets; ++i) cmax = tab.C[i] > cmax ? tab.C[i] : cmax;
+  // privatised histogram: up to 24 KB of replicas for small C, one replica up to 96 KB, global atomics beyond
+  size_t smem = (size_t)cmax * cmax * 4;
+  if (smem < 24 * 1024) smem = 24 * 1024;
+  if (smem > 96 * 1024) smem = 24 * 1024;
+  auto k = confusion_images_kernel<L, P>;
+  if (smem > 48 * 1024) MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = ceil_div64(ceil_div64(ppi, kPx), 256);
+  const int64_t cap = ceil_div64((int64_t)sm_count() * per_sm, n_images);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k<<<dim3((unsigned)blocks, (unsigned)n_images), 256, smem, st>>>(
+      (const L*)label, (const P*)pred, luts, ids, ppi, reinterpret_cast<unsigned long long*>(hist), tab, ignore,
+      err_flag, (int)(smem / 4));
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+
+template <typename L>
+int dispatch_pred_images(const void* label, const void* pred, int pred_dtype, const uint8_t* luts, const int32_t* ids,
+                         int n_images, int64_t ppi, int64_t* hist, const mdseg_hist_table& tab, int ignore,
+                         int32_t* err_flag, cudaStream_t st) {
+  switch (pred_dtype) {
+    case MDSEG_U8: return launch_images<L, uint8_t>(label, pred, luts, ids, n_images, ppi, hist, tab, ignore, err_flag, st);
+    case MDSEG_I32: return launch_images<L, int32_t>(label, pred, luts, ids, n_images, ppi, hist, tab, ignore, err_flag, st);
+    case MDSEG_I64: return launch_images<L, int64_t>(label, pred, luts, ids, n_images, ppi, hist, tab, ignore, err_flag, st);
+  }
+  set_error("mdseg_confusion_images: unsupported pred_dtype %d", pred_dtype);
+  return 2;
+}
+
 template <typename L, typename P>
 int launch(const void* label, const void* pred, const uint8_t* lut, int64_t* hist, int Ca, int Cb, int ignore,
            int64_t n, int32_t* err_flag, cudaStream_t st) {
@@ -231,6 +363,42 @@ extern "C" int mdseg_miou(const int64_t* hist, int C, float* iou, float* miou, v
   using namespace mdseg;
   MDSEG_REQUIRE(hist && iou && C > 0, "mdseg_miou: bad arguments (iou is required)");
   miou_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const long long*)hist, C, iou, miou);
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int mdseg_confusion_images(const void* label, int label_dtype, const void* pred, int pred_dtype,
+                                      const uint8_t* luts, const int32_t* dataset_ids, int n_images,
+                                      int64_t px_per_image, int64_t* hist, const mdseg_hist_table* tab, int ignore,
+                                      int32_t* err_flag, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(tab && tab->n_datasets > 0 && tab->n_datasets <= MDSEG_MAX_DATASETS, "mdseg_confusion_images: bad table");
+  for (int i = 0; i < tab->n_datasets; ++i)
+    MDSEG_REQUIRE(tab->C[i] > 0 && tab->C[i] < 32768 && tab->offset[i] >= 0, "mdseg_confusion_images: bad table entry %d", i);
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && px_per_image >= 0, "mdseg_confusion_images: bad shape");
+  if (n_images == 0 || px_per_image == 0) return 0;
+  MDSEG_REQUIRE(label && pred && hist && err_flag, "mdseg_confusion_images: null pointer (err_flag is required)");
+  MDSEG_REQUIRE(px_per_image % 16 == 0 && (((uintptr_t)label | (uintptr_t)pred) & 15) == 0,
+                "mdseg_confusion_images: images must be 16-element multiples and 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (label_dtype) {
+    case MDSEG_U8: return dispatch_pred_images<uint8_t>(label, pred, pred_dtype, luts, dataset_ids, n_images, px_per_image, hist, *tab, ignore, err_flag, st);
+    case MDSEG_I32: return dispatch_pred_images<int32_t>(label, pred, pred_dtype, luts, dataset_ids, n_images, px_per_image, hist, *tab, ignore, err_flag, st);
+    case MDSEG_I64: return dispatch_pred_images<int64_t>(label, pred, pred_dtype, luts, dataset_ids, n_images, px_per_image, hist, *tab, ignore, err_flag, st);
+  }
+  set_error("mdseg_confusion_images: unsupported label_dtype %d", label_dtype);
+  return 2;
+}
+
+extern "C" int mdseg_miou_images(const int64_t* hist, const mdseg_hist_table* tab, float* iou, int iou_stride,
+                                 float* miou, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(hist && tab && iou && miou && tab->n_datasets > 0 && tab->n_datasets <= MDSEG_MAX_DATASETS,
+                "mdseg_miou_images: bad arguments");
+  for (int i = 0; i < tab->n_datasets; ++i)
+    MDSEG_REQUIRE(tab->C[i] > 0 && tab->C[i] <= iou_stride, "mdseg_miou_images: iou_stride %d < C[%d]", iou_stride, i);
+  miou_images_kernel<<<tab->n_datasets, 256, 0, (cudaStream_t)stream>>>((const long long*)hist, *tab, iou, iou_stride,
+                                                                      miou);
   MDSEG_LAUNCH_OK();
   return 0;
 }

@@ -66,11 +66,22 @@ template <> struct Pack16<int64_t> {
   }
 };
 
+// blockIdx.y = image: `n` elements per image; image b uses table lut + 256 * lut_ids[b] (lut_ids NULL: table 0).
+// An id outside [0, n_luts) maps the whole image to `oob` and raises MDSEG_ERR_DATASET_ID.
 template <typename In, typename Out>
 __global__ void __launch_bounds__(256) lut_remap_kernel(const In* __restrict__ in, Out* __restrict__ out,
-                                                       const uint8_t* __restrict__ lut, int oob, int64_t n) {
+                                                       const uint8_t* __restrict__ lut, int oob, int64_t n,
+                                                       const int32_t* __restrict__ lut_ids, int n_luts,
+                                                       int* err_flag) {
   __shared__ uint8_t s_lut[256];
-  s_lut[threadIdx.x] = lut[threadIdx.x];
+  {
+    const int id = lut_ids ? lut_ids[blockIdx.y] : 0;
+    const bool ok = id >= 0 && id < n_luts;
+    s_lut[threadIdx.x] = ok ? lut[(int64_t)id * 256 + threadIdx.x] : (uint8_t)oob;
+    if (!ok && threadIdx.x == 0 && blockIdx.x == 0 && err_flag) atomicOr(err_flag, MDSEG_ERR_DATASET_ID);
+    in += (int64_t)blockIdx.y * n;
+    out += (int64_t)blockIdx.y * n;
+  }
   __syncthreads();
 
   const int64_t nvec = n / kE;
@@ -101,9 +112,18 @@ __global__ void __launch_bounds__(256) lut_remap_kernel(const In* __restrict__ i
 // Unaligned fallback: one element per thread.
 template <typename In, typename Out>
 __global__ void __launch_bounds__(256) lut_remap_scalar_kernel(const In* __restrict__ in, Out* __restrict__ out,
-                                                              const uint8_t* __restrict__ lut, int oob, int64_t n) {
+                                                              const uint8_t* __restrict__ lut, int oob, int64_t n,
+                                                              const int32_t* __restrict__ lut_ids, int n_luts,
+                                                              int* err_flag) {
   __shared__ uint8_t s_lut[256];
-  s_lut[threadIdx.x] = lut[threadIdx.x];
+  {
+    const int id = lut_ids ? lut_ids[blockIdx.y] : 0;
+    const bool ok = id >= 0 && id < n_luts;
+    s_lut[threadIdx.x] = ok ? lut[(int64_t)id * 256 + threadIdx.x] : (uint8_t)oob;
+    if (!ok && threadIdx.x == 0 && blockIdx.x == 0 && err_flag) atomicOr(err_flag, MDSEG_ERR_DATASET_ID);
+    in += (int64_t)blockIdx.y * n;
+    out += (int64_t)blockIdx.y * n;
+  }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -113,33 +133,37 @@ __global__ void __launch_bounds__(256) lut_remap_scalar_kernel(const In* __restr
 }
 
 template <typename In, typename Out>
-int launch(const void* in, void* out, const uint8_t* lut, int oob, int64_t n, cudaStream_t st) {
-  if (n == 0) return 0;
-  const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+int launch(const void* in, void* out, const uint8_t* lut, int oob, int64_t n, cudaStream_t st,
+           const int32_t* lut_ids = nullptr, int n_luts = 1, int n_images = 1, int* err_flag = nullptr) {
+  if (n == 0 || n_images == 0) return 0;
+  // per-image slices keep the 16-byte alignment only when the image size is a multiple of 16 elements
+  const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && (n_images == 1 || n % kE == 0);
   const int sms = sm_count();
+  const int64_t cap = ceil_div64((int64_t)sms * 8, n_images);
   if (aligned) {
     int64_t nvec = n / kE;
     int64_t blocks = ceil_div64(nvec > 0 ? nvec : 1, 256);
-    int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    lut_remap_kernel<In, Out><<<(unsigned)blocks, 256, 0, st>>>((const In*)in, (Out*)out, lut, oob, n);
+    lut_remap_kernel<In, Out><<<dim3((unsigned)blocks, (unsigned)n_images), 256, 0, st>>>(
+        (const In*)in, (Out*)out, lut, oob, n, lut_ids, n_luts, err_flag);
   } else {
     int64_t blocks = ceil_div64(n, 256);
-    int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
-    lut_remap_scalar_kernel<In, Out><<<(unsigned)blocks, 256, 0, st>>>((const In*)in, (Out*)out, lut, oob, n);
+    lut_remap_scalar_kernel<In, Out><<<dim3((unsigned)blocks, (unsigned)n_images), 256, 0, st>>>(
+        (const In*)in, (Out*)out, lut, oob, n, lut_ids, n_luts, err_flag);
   }
   MDSEG_LAUNCH_OK();
   return 0;
 }
 
 template <typename In>
-int dispatch_out(const void* in, void* out, int out_dtype, const uint8_t* lut, int oob, int64_t n, cudaStream_t st) {
+int dispatch_out(const void* in, void* out, int out_dtype, const uint8_t* lut, int oob, int64_t n, cudaStream_t st,
+                 const int32_t* lut_ids = nullptr, int n_luts = 1, int n_images = 1, int* err_flag = nullptr) {
   switch (out_dtype) {
-    case MDSEG_U8: return launch<In, uint8_t>(in, out, lut, oob, n, st);
-    case MDSEG_I32: return launch<In, int32_t>(in, out, lut, oob, n, st);
-    case MDSEG_I64: return launch<In, int64_t>(in, out, lut, oob, n, st);
+    case MDSEG_U8: return launch<In, uint8_t>(in, out, lut, oob, n, st, lut_ids, n_luts, n_images, err_flag);
+    case MDSEG_I32: return launch<In, int32_t>(in, out, lut, oob, n, st, lut_ids, n_luts, n_images, err_flag);
+    case MDSEG_I64: return launch<In, int64_t>(in, out, lut, oob, n, st, lut_ids, n_luts, n_images, err_flag);
   }
   set_error("mdseg_lut_remap: unsupported out_dtype %d", out_dtype);
   return 2;
@@ -160,5 +184,23 @@ extern "C" int mdseg_lut_remap(const void* in, int in_dtype, void* out, int out_
     case MDSEG_I64: return dispatch_out<int64_t>(in, out, out_dtype, lut256, oob, n, st);
   }
   set_error("mdseg_lut_remap: unsupported in_dtype %d", in_dtype);
+  return 2;
+}
+
+extern "C" int mdseg_lut_remap_images(const void* in, int in_dtype, void* out, int out_dtype, const uint8_t* luts,
+                                      int n_luts, const int32_t* lut_ids, int oob, int n_images,
+                                      int64_t px_per_image, int32_t* err_flag, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && px_per_image >= 0 && n_luts > 0,
+                "mdseg_lut_remap_images: bad shape");
+  if (n_images == 0 || px_per_image == 0) return 0;
+  MDSEG_REQUIRE(in && out && luts, "mdseg_lut_remap_images: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (in_dtype) {
+    case MDSEG_U8: return dispatch_out<uint8_t>(in, out, out_dtype, luts, oob, px_per_image, st, lut_ids, n_luts, n_images, err_flag);
+    case MDSEG_I32: return dispatch_out<int32_t>(in, out, out_dtype, luts, oob, px_per_image, st, lut_ids, n_luts, n_images, err_flag);
+    case MDSEG_I64: return dispatch_out<int64_t>(in, out, out_dtype, luts, oob, px_per_image, st, lut_ids, n_luts, n_images, err_flag);
+  }
+  set_error("mdseg_lut_remap_images: unsupported in_dtype %d", in_dtype);
   return 2;
 }

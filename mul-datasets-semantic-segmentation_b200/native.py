@@ -50,6 +50,10 @@ class SparseGraph(C.Structure):
     ]
 
 
+class HistTable(C.Structure):
+    _fields_ = [("n_datasets", C.c_int), ("C", C.c_int * MAX_DATASETS), ("offset", C.c_longlong * MAX_DATASETS)]
+
+
 class GraphTable(C.Structure):
     _fields_ = [("g", SparseGraph * MAX_DATASETS), ("n_datasets", C.c_int), ("C_uni", C.c_int)]
 
@@ -64,6 +68,9 @@ SIGNATURES = {
     "mdseg_lut_remap": (_I, [_P, _I, _P, _I, _P, _I, _L, _P]),
     "mdseg_confusion": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _L, _P, _P]),
     "mdseg_miou": (_I, [_P, _I, _P, _P, _P]),
+    "mdseg_lut_remap_images": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _L, _P, _P]),
+    "mdseg_confusion_images": (_I, [_P, _I, _P, _I, _P, _P, _I, _L, _P, C.POINTER(HistTable), _I, _P, _P]),
+    "mdseg_miou_images": (_I, [_P, C.POINTER(HistTable), _P, _I, _P, _P]),
     "mdseg_ohem_state_bytes": (C.c_size_t, []),
     "mdseg_select_workspace_bytes": (C.c_size_t, [_I]),
     "mdseg_ohem_begin": (_I, [_P, _I, _F, _P]),

@@ -135,6 +135,76 @@ def miou(hist):
     return iou, m
 
 
+# ---- a1 / a12 / a13 for a whole multi-dataset batch: one launch each ---------------------------------------
+def lut_remap_images(x, luts, lut_ids, out_dtype=None, oob=255):
+    """out[b] = luts[lut_ids[b]][x[b]] for a batch [B, H, W] holding images of several datasets
+    (one lb_map per dataset, lib/base_dataset.py:81-82).  luts: uint8 [n_luts, 256]."""
+    _require_cuda(x)
+    x = x.contiguous()
+    if x.dtype not in (torch.uint8, torch.int32, torch.int64):
+        raise TypeError(f"lut_remap_images: unsupported input dtype {x.dtype}")
+    out_dtype = out_dtype or x.dtype
+    luts = torch.as_tensor(luts).to(device=x.device, dtype=torch.uint8).contiguous()
+    if luts.dim() != 2 or luts.shape[1] != 256:
+        raise ValueError("luts must be [n_luts, 256]")
+    B = x.shape[0]
+    ids = _ids32(lut_ids, B, x.device)
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    N.call("mdseg_lut_remap_images", _ptr(x), _DT[x.dtype], _ptr(out), _DT[out_dtype], _ptr(luts), luts.shape[0],
+           _ptr(ids), int(oob), B, x[0].numel() if B else 0, _ptr(err_flag(x.device)), _stream())
+    return out
+
+
+def _hist_table(n_cats):
+    tab = N.HistTable()
+    tab.n_datasets = len(n_cats)
+    off = 0
+    for i, c in enumerate(n_cats):
+        tab.C[i], tab.offset[i] = int(c), off
+        off += int(c) * int(c)
+    return tab, off
+
+
+def confusion_images(label, pred, dataset_ids, n_cats, luts=None, ignore=255, hist=None):
+    """Per-dataset square confusion matrices of a multi-dataset batch in ONE launch.  Returns (flat int64
+    accumulator, [views [C_d, C_d]]); `hist` (flat) is accumulated into when given (evaluate.py:89-93)."""
+    _require_cuda(label, pred)
+    label, pred = _labels(label), _labels(pred)
+    if label.shape != pred.shape:
+        raise ValueError("label / pred shape mismatch")
+    tab, total = _hist_table(n_cats)
+    if hist is None:
+        hist = torch.zeros(total, dtype=torch.int64, device=label.device)
+    B = label.shape[0]
+    ppi = label[0].numel() if B else 0
+    if luts is not None:
+        luts = torch.as_tensor(luts).to(device=label.device, dtype=torch.uint8).contiguous()
+    if ppi % 16 or label.data_ptr() % 16 or pred.data_ptr() % 16:  # ragged images: one call per image
+        ids = [int(v) for v in torch.as_tensor(dataset_ids).tolist()]
+        for b, d in enumerate(ids):
+            confusion(label[b], pred[b], n_cats[d], lut=None if luts is None else luts[d], ignore=ignore,
+                      hist=hist[tab.offset[d]:tab.offset[d] + n_cats[d] ** 2].view(n_cats[d], n_cats[d]))
+    else:
+        ids = _ids32(dataset_ids, B, label.device)
+        N.call("mdseg_confusion_images", _ptr(label), _DT[label.dtype], _ptr(pred), _DT[pred.dtype], _ptr(luts),
+               _ptr(ids), B, ppi, _ptr(hist), C.byref(tab), int(ignore), _ptr(err_flag(label.device)), _stream())
+    views = [hist[tab.offset[i]:tab.offset[i] + c * c].view(c, c) for i, c in enumerate(n_cats)]
+    return hist, views
+
+
+def miou_images(hist, n_cats):
+    """(iou [n_datasets, max C] (NaN padded), miou [n_datasets]) from the flat accumulator of confusion_images."""
+    _require_cuda(hist)
+    tab, total = _hist_table(n_cats)
+    if hist.numel() != total or hist.dtype != torch.int64:
+        raise ValueError("hist must be the flat int64 accumulator of confusion_images")
+    cm = max(n_cats)
+    iou = torch.full((len(n_cats), cm), float("nan"), dtype=torch.float32, device=hist.device)
+    m = torch.empty(len(n_cats), dtype=torch.float32, device=hist.device)
+    N.call("mdseg_miou_images", _ptr(hist.contiguous()), C.byref(tab), _ptr(iou), cm, _ptr(m), _stream())
+    return iou, m
+
+
 # ---- OHEM state helpers ----------------------------------------------------------------
 def _new_states(n, thresh, device):
     st = torch.empty(n * STATE_BYTES, dtype=torch.uint8, device=device)

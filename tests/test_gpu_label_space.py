@@ -132,3 +132,46 @@ def test_label_nearest(ops, shape, size):
     lab = rng.integers(0, 256, shape)
     got = ops.label_nearest(torch.from_numpy(lab).to(DEV), size)
     assert np.array_equal(got.cpu().numpy(), ls.nearest_resize(lab, size))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lab_dt", [torch.int64, torch.uint8])
+@pytest.mark.parametrize("shape", [(5, 16, 48), (4, 37, 53), (3, 64, 128)])
+def test_batched_label_space_ops(ops, lab_dt, shape):
+    """lut_remap_images / confusion_images / miou_images == the per-dataset calls == the numpy oracle."""
+    g = torch.Generator().manual_seed(11)
+    B, H, W = shape
+    n_cats = [19, 7, 150]
+    ids = torch.randint(0, 3, (B,), generator=g).tolist()
+    luts = np.stack([np.where(np.arange(256) < 250, np.arange(256) % c, 255).astype(np.uint8) for c in n_cats])
+    raw = torch.randint(0, 256, (B, H, W), generator=g, dtype=torch.uint8)
+    pred = torch.stack([torch.randint(0, n_cats[d], (H, W), generator=g) for d in ids])
+    lab = ops.lut_remap_images(raw.to(DEV), luts, ids, out_dtype=lab_dt)
+    want_lab = np.stack([ls.lut_gather(raw[b].numpy(), luts[d]) for b, d in enumerate(ids)])
+    assert np.array_equal(lab.cpu().numpy().astype(np.int64), want_lab.astype(np.int64))
+    hist, views = ops.confusion_images(lab, pred.to(DEV), ids, n_cats)
+    iou, miou = ops.miou_images(hist, n_cats)
+    for d, c in enumerate(n_cats):
+        sel = [b for b in range(B) if ids[b] == d]
+        want = np.zeros((c, c), dtype=np.int64)
+        for b in sel:
+            want += ls.confusion(want_lab[b], pred[b].numpy(), c)
+        assert np.array_equal(views[d].cpu().numpy(), want), d
+        w_iou, w_miou = ls.ious_miou(want)
+        got = iou[d, :c].cpu().numpy()
+        assert np.allclose(got, w_iou, rtol=1e-6, atol=0, equal_nan=True)
+        assert (np.isnan(w_miou) and np.isnan(float(miou[d]))) or abs(float(miou[d]) - w_miou) <= 1e-6
+    # the LUT can also be fused into the histogram pass (raw ids in, evaluate-time remap)
+    hist2, _ = ops.confusion_images(raw.to(DEV), pred.to(DEV), ids, n_cats, luts=luts)
+    assert torch.equal(hist, hist2)
+    ops.check_errors(DEV)
+
+
+@pytest.mark.gpu
+def test_batched_ops_flag_bad_dataset_id(ops):
+    raw = torch.zeros(2, 16, 16, dtype=torch.uint8, device=DEV)
+    luts = np.zeros((2, 256), dtype=np.uint8)
+    out = ops.lut_remap_images(raw, luts, [0, 5], oob=255)
+    assert int(out[1].min()) == 255 and int(out[0].max()) == 0
+    with pytest.raises(RuntimeError, match="dataset id"):
+        ops.check_errors(DEV)
