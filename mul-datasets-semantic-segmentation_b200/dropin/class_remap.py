@@ -1,0 +1,96 @@
+"""Drop-in for lib/class_remap.py ``ClassRemap`` (:8-232): label-space remaps as 256-entry LUT gathers.
+
+The reference applies one compare + masked write per class (19-150 full-tensor passes per call); every
+one of those remaps is ``out = lut[labels]`` with a uint8[256] table built once from the same
+``class_remap{i}`` config dicts.  Return types match the reference: tensors of the input's dtype / shape
+(lists of them for SegRemapping), fp32 remap matrices.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+CITY_ID = 0
+CAM_ID = 1
+
+
+class ClassRemap:
+    def __init__(self, configer=None):
+        self.configer = configer
+        self.ignore_index = self.configer.get('loss', 'ignore_index')
+        self.num_unify_classes = self.configer.get('num_unify_classes')
+        self.remapList = []
+        self.maxMapNums = []
+        self._unpack()
+
+    # ---- config parsing (class_remap.py:146-183) ----------------------------------------------
+    def _unpack(self):
+        if not self.configer.exists('n_datasets'):
+            raise NotImplementedError("read json errror! no  n_datasets")
+        self.n_datasets = self.configer.get('n_datasets')
+        for i in range(1, self.n_datasets + 1):
+            if not self.configer.exists('class_remap' + str(i)):
+                raise NotImplementedError("read json errror! no class_remap" + str(i))
+            raw = self.configer.get('class_remap' + str(i))
+            remap, class_id, mx = {}, 0, 0
+            while str(class_id) in raw:
+                remap[class_id] = list(raw[str(class_id)])
+                mx = max(mx, len(remap[class_id]))
+                class_id += 1
+            self.remapList.append(remap)
+            self.maxMapNums.append(mx)
+        self.class_remap_matrixs = []
+        for i in range(self.n_datasets):
+            n_cats = self.configer.get('dataset' + str(i + 1), 'n_cats')
+            m = torch.zeros([n_cats, self.num_unify_classes], dtype=torch.float32)
+            for k, v in self.remapList[i].items():
+                m[k, v] = 1
+            self.class_remap_matrixs.append(m)
+        # the LUT form of every remap
+        ign = self.ignore_index
+        self._single_luts, self._seg_luts, self._reverse_luts = [], [], []
+        for d, remap in enumerate(self.remapList):
+            single = np.full(256, ign, dtype=np.uint8)
+            for k, v in remap.items():
+                if len(v) == 1 and 0 <= int(k) < 256:
+                    single[int(k)] = v[0]
+            self._single_luts.append(single)
+            segs = []
+            for j in range(self.maxMapNums[d]):
+                lut = np.full(256, ign, dtype=np.uint8)
+                for k, v in remap.items():
+                    if len(v) > j and 0 <= int(k) < 256:
+                        lut[int(k)] = v[j]
+                segs.append(lut)
+            self._seg_luts.append(segs)
+            rev = np.zeros(256, dtype=np.uint8)
+            for k, v in remap.items():  # dict order; later keys overwrite (class_remap.py:189-203)
+                if (d == CITY_ID and k == 19) or (d == CAM_ID and k == 12):
+                    break
+                for lb in v:
+                    if 0 <= int(lb) < 256:
+                        rev[int(lb)] = int(k)
+            self._reverse_luts.append(rev)
+
+    # ---- queries ------------------------------------------------------------------------------
+    def IsSingleRemaplb(self, lb):
+        return any(len(v) == 1 and v[0] == lb for remap in self.remapList for v in remap.values())
+
+    def getAnyClassRemap(self, lb_id, dataset_id):
+        return self.remapList[dataset_id][lb_id]
+
+    def getRemapMatrix(self, dataset_id):
+        return self.class_remap_matrixs[dataset_id]
+
+    # ---- remaps (device LUT gathers) ----------------------------------------------------------------
+    def SingleSegRemapping(self, labels, dataset_id):
+        """Only classes with exactly one unified target are mapped; everything else -> ignore_index (:34-48)."""
+        return ops.lut_remap(labels, self._single_luts[dataset_id], oob=self.ignore_index)
+
+    def SegRemapping(self, labels, dataset_id):
+        """List of maxMapNums[dataset_id] maps; the j-th holds v[j] where len(v) > j, else ignore_index (:50-66)."""
+        return [ops.lut_remap(labels, lut, oob=self.ignore_index) for lut in self._seg_luts[dataset_id]]
+
+    def ReverseSegRemap(self, preds, dataset_id):
+        """Unified-space predictions -> dataset classes; unmapped ids -> 0 (:189-203)."""
+        return ops.lut_remap(preds, self._reverse_luts[dataset_id], oob=0)

@@ -286,6 +286,72 @@ def ohem_ce_with_state(logits, labels, thresh, ignore=255):
         return loss, ctx.saved[2], read_states(ctx.saved[4])[0]
 
 
+# ---- MdsOhemCELoss on full-resolution per-dataset logits (the reference module's own call form) ---------------
+class _MdsOhemCEFull(torch.autograd.Function):
+    """One OHEM selection over the concatenation of per-dataset CE vectors (lib/loss/ohem_ce_loss.py:48-90).
+    logits[k]: [B_k, C_k, H, W]; labels[k]: [B_k, H, W], in the same (ascending dataset id) order."""
+
+    @staticmethod
+    def forward(ctx, thresh, ignore, n, *tensors):
+        logits, labels = list(tensors[:n]), [_labels(t) for t in tensors[n:]]
+        _require_cuda(*logits, *labels)
+        dev = logits[0].device
+        H, W = logits[0].shape[2:]
+        metas, offs, P = [], [], 0
+        for k in range(n):
+            lg = logits[k]
+            if lg.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+                lg = lg.float()
+            if lg.is_contiguous():
+                layout = N.NCHW
+            elif lg.is_contiguous(memory_format=torch.channels_last):
+                layout = N.NHWC
+            else:
+                lg, layout = lg.contiguous(), N.NCHW
+            if tuple(lg.shape[2:]) != (H, W) or labels[k].numel() != lg.shape[0] * H * W:
+                raise ValueError("every dataset's logits / labels must share H x W")
+            logits[k] = lg
+            metas.append(layout)
+            offs.append(P)
+            P += lg.shape[0] * H * W
+        loss_px = torch.empty(P, dtype=torch.float32, device=dev)
+        lse_px = torch.empty(P, dtype=torch.float32, device=dev)
+        st = _new_states(1, thresh, dev)
+        for k in range(n):
+            lg = logits[k]
+            N.call("mdseg_ohem_ce_fwd", _ptr(lg), _DT[lg.dtype], metas[k], _ptr(labels[k]), _DT[labels[k].dtype],
+                   lg.shape[0], lg.shape[1], H, W, int(ignore), loss_px.data_ptr() + 4 * offs[k],
+                   lse_px.data_ptr() + 4 * offs[k], _ptr(st), _ptr(err_flag(dev)), _stream())
+        out = _select(loss_px, P // (H * W), H * W, None, st, 1)
+        ctx.save_for_backward(loss_px, lse_px, st, *logits, *labels)
+        ctx.meta = (n, metas, offs, int(ignore), H, W)
+        ctx.states = st
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        n, metas, offs, ignore, H, W = ctx.meta
+        loss_px, lse_px, st = ctx.saved_tensors[:3]
+        logits, labels = ctx.saved_tensors[3:3 + n], ctx.saved_tensors[3 + n:]
+        g = _grad_scalar(grad_out)
+        grads = []
+        for k in range(n):
+            lg = logits[k]
+            dl = torch.empty_like(lg)
+            N.call("mdseg_ohem_ce_bwd", _ptr(lg), _DT[lg.dtype], metas[k], _ptr(labels[k]), _DT[labels[k].dtype],
+                   lg.shape[0], lg.shape[1], H, W, ignore, loss_px.data_ptr() + 4 * offs[k],
+                   lse_px.data_ptr() + 4 * offs[k], _ptr(st), _ptr(g), 1.0, _ptr(dl), _stream())
+            grads.append(dl)
+        return (None, None, None, *grads, *([None] * n))
+
+
+def mds_ohem_ce_full(logits, labels, thresh, ignore=255):
+    """logits: list of [B_k, C_k, H, W]; labels: list of [B_k, H, W] — one OHEM selection over all of them."""
+    if not logits:
+        return torch.tensor(float("nan"))
+    return _MdsOhemCEFull.apply(float(thresh), int(ignore), len(logits), *logits, *labels)
+
+
 # ---- bipartite graphs: host-side cache of the CSR / CSC device images -------------------------
 class BipartiteGraphs:
     """Device descriptors of bi_graphs[i] ([C_ds_i, C_uni]) for mdseg_proj_*.

@@ -1,0 +1,153 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/mdseg.h declares,
+the ctypes mirror matches the C structs, the drop-in modules import and parse configs, and the N > 1 logic
+(image sharding, int64 histogram all-reduce, max-over-ranks timing) works under gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mdseg.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdseg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mdseg_b200 import native
+    names = _declared_symbols()
+    assert len(names) >= 25
+    lib = ctypes.CDLL(native.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    unbound = [n for n in names if n not in native.SIGNATURES]
+    assert not unbound, f"declared in mdseg.h but not bound in native.py: {unbound}"
+    assert native.version() == 100
+
+
+def test_struct_mirrors_match_the_c_layout(tmp_path):
+    """sizeof() of every by-value struct as gcc sees it == the ctypes mirror."""
+    from mdseg_b200 import native
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include "mdseg.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                    'sizeof(mdseg_ohem_state),sizeof(mdseg_src_table),sizeof(mdseg_sparse_graph),'
+                    'sizeof(mdseg_graph_table),sizeof(mdseg_hist_table));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(native.OhemState), ctypes.sizeof(native.SrcTable), ctypes.sizeof(native.SparseGraph),
+            ctypes.sizeof(native.GraphTable), ctypes.sizeof(native.HistTable)]
+    assert got == want
+
+
+def test_ops_refuse_cpu_tensors():
+    from mdseg_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.lut_remap(torch.zeros(4, dtype=torch.uint8), np.arange(256, dtype=np.uint8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.ohem_ce(torch.zeros(1, 2, 2, 2), torch.zeros(1, 2, 2, dtype=torch.long), 0.35)
+
+
+class DictConfiger:
+    """Minimal stand-in for tools/configer.py:Configer (get / exists over nested dicts)."""
+
+    def __init__(self, d):
+        self.d = d
+
+    def exists(self, *key):
+        cur = self.d
+        for k in key:
+            if not isinstance(cur, dict) or k not in cur:
+                return False
+            cur = cur[k]
+        return True
+
+    def get(self, *key):
+        cur = self.d
+        for k in key:
+            cur = cur[k]
+        return cur
+
+
+def test_dropin_modules_install_and_parse_configs():
+    import json
+    import mdseg_b200.dropin as dropin
+    mods = dropin.install(extra=[("lib.loss.loss_cross_datasets", "loss_cross_datasets")])
+    try:
+        from lib.loss.ohem_ce_loss import MdsOhemCELoss, OhemCELoss
+        from lib.class_remap import ClassRemap
+        crit = OhemCELoss(0.7)
+        assert abs(float(crit.thresh) - 0.35667494) < 1e-7 and crit.ignore_lb == 255
+        cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "test_test.json")))
+        cfg.setdefault("loss", {}).setdefault("ignore_index", 255)
+        cr = ClassRemap(DictConfiger(cfg))
+        z = np.load(os.path.join(ROOT, "tests", "golden", "class_remap.npz"))
+        for d in range(cr.n_datasets):
+            assert np.array_equal(cr.getRemapMatrix(d).numpy(), z[f"test_d{d}_matrix"])
+        assert [cr.IsSingleRemaplb(u) for u in range(cr.num_unify_classes)] == list(z["test_single_lbs"])
+        assert MdsOhemCELoss(DictConfiger({"n_datasets": 2}), 0.4).n_datasets == 2
+    finally:
+        for name in mods:
+            sys.modules.pop(name, None)
+
+
+def test_shard_images_partitions_the_batch():
+    from mdseg_b200.dist_utils import shard_images
+    for n in (0, 1, 7, 16, 33):
+        for w in (1, 2, 3, 8):
+            parts = [list(shard_images(n, r, w)) for r in range(w)]
+            assert sum(parts, []) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from mdseg_b200 import dist_utils as du
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        assert du.world() == (rank, world)
+        # every rank histograms its own shard of the images; the all-reduce must equal the global histogram
+        g = torch.Generator().manual_seed(5)
+        C, n_images, px = 7, 5, 4096
+        label = torch.randint(0, C, (n_images, px), generator=g)
+        pred = torch.randint(0, C, (n_images, px), generator=g)
+        label[torch.rand(n_images, px, generator=g) < 0.1] = 255
+        mine = list(du.shard_images(n_images, rank, world))
+        hist = torch.zeros(C, C, dtype=torch.int64)
+        for b in mine:
+            keep = label[b] != 255
+            hist += torch.bincount(label[b][keep] * C + pred[b][keep], minlength=C * C).view(C, C)
+        hist[0, 0] += (1 << 40) + rank  # far beyond float32's exact range: the reduction must stay integer
+        du.allreduce_hist(hist)
+        keep = label != 255
+        want = torch.bincount(label[keep] * C + pred[keep], minlength=C * C).view(C, C)
+        want[0, 0] += world * (1 << 40) + sum(range(world))
+        assert torch.equal(hist, want)
+        with pytest.raises(TypeError):
+            du.allreduce_hist(hist.float())
+        # a step is as slow as the slowest rank; the whole-job rate counts every rank's pixels
+        ms = du.max_over_ranks(10.0 + rank)
+        assert ms == 10.0 + world - 1
+        assert du.whole_job_rate(1000, world, ms) == 1000 * world / (ms * 1e-3)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
