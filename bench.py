@@ -164,7 +164,7 @@ KERNELS_PER_CALL = {"mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "m
 
 
 def run_ours(args, rank, world, local_rank):
-    from mdseg_b200 import native, ops  # raises if libmdseg_b200.so is missing: no fallback
+    from mdseg_b200 import dist_utils, native, ops  # raises if libmdseg_b200.so is missing: no fallback
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
@@ -213,8 +213,7 @@ def run_ours(args, rank, world, local_rank):
         # a12/a13: confusion matrices of every dataset (one launch) + mIoU
         hist_flat.zero_()
         ops.confusion_images(labels, pred, ids_t, n_cats, hist=hist_flat)
-        if world > 1:
-            dist.all_reduce(hist_flat)  # one int64 all-reduce for all datasets (evaluate.py:187-188)
+        dist_utils.allreduce_hist(hist_flat)  # one int64 all-reduce for all datasets (evaluate.py:187-188)
         _, mious = ops.miou_images(hist_flat, n_cats)
         out["loss"], out["miou"] = loss.detach(), mious
 
