@@ -199,28 +199,56 @@ confusion_images_kernel(const L* __restrict__ label, const P* __restrict__ pred,
   }
 }
 
-// iou / mIoU of every dataset: one CTA per dataset (see miou_kernel)
-__global__ void miou_images_kernel(const long long* __restrict__ hist, const mdseg_hist_table tab,
-                                   float* __restrict__ iou, int iou_stride, float* __restrict__ miou) {
+// iou / mIoU of every dataset: one CTA per dataset.  Row / column sums are coalesced (a warp walks a row,
+// lanes walk columns); the nanmean is a fixed-shape shuffle tree in double, so it is run-to-run deterministic.
+__global__ void __launch_bounds__(256) miou_images_kernel(const long long* __restrict__ hist, const mdseg_hist_table tab,
+                                                          float* __restrict__ iou, int iou_stride,
+                                                          float* __restrict__ miou) {
+  extern __shared__ long long s_sum[];  // [2][C]: row sums, column sums
   const int d = blockIdx.x;
   const int C = tab.C[d];
   const long long* h = hist + tab.offset[d];
   float* io = iou + (int64_t)d * iou_stride;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    long long row = 0, col = 0;
-    for (int j = 0; j < C; ++j) { row += h[(int64_t)c * C + j]; col += h[(int64_t)j * C + c]; }
-    const long long dg = h[(int64_t)c * C + c];
-    io[c] = (float)((double)dg / (double)(col + row - dg));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  long long* rows = s_sum;
+  long long* cols = s_sum + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) cols[c] = 0;
+  __syncthreads();
+  for (int r = warp; r < C; r += n_warps) {  // warp r-th row: coalesced; column partials kept per lane
+    long long acc = 0;
+    for (int j = lane; j < C; j += 32) {
+      const long long v = h[(int64_t)r * C + j];
+      acc += v;
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&cols[j]), (unsigned long long)v);  // integer: exact
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rows[r] = acc;
   }
+  __syncthreads();
+  double part = 0.0;
+  int cnt = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const long long dg = h[(int64_t)c * C + c];
+    // evaluate.py:96: diag / (sum0 + sum1 - diag); 0/0 -> NaN (class absent)
+    const float v = (float)((double)dg / (double)(cols[c] + rows[c] - dg));
+    io[c] = v;
+    if (v == v) { part += (double)v; ++cnt; }
+  }
+  __shared__ double s_part[8];
+  __shared__ int s_cnt[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) { s_part[warp] = part; s_cnt[warp] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double sum = 0.0;
-    int cnt = 0;
-    for (int c = 0; c < C; ++c) {
-      const float v = io[c];
-      if (v == v) { sum += (double)v; ++cnt; }
-    }
-    miou[d] = cnt ? (float)(sum / cnt) : __int_as_float(0x7fc00000);
+    int n = 0;
+    for (int w = 0; w < n_warps; ++w) { sum += s_part[w]; n += s_cnt[w]; }
+    miou[d] = n ? (float)(sum / n) : __int_as_float(0x7fc00000);
   }
 }
 
@@ -397,8 +425,11 @@ extern "C" int mdseg_miou_images(const int64_t* hist, const mdseg_hist_table* ta
                 "mdseg_miou_images: bad arguments");
   for (int i = 0; i < tab->n_datasets; ++i)
     MDSEG_REQUIRE(tab->C[i] > 0 && tab->C[i] <= iou_stride, "mdseg_miou_images: iou_stride %d < C[%d]", iou_stride, i);
-  miou_images_kernel<<<tab->n_datasets, 256, 0, (cudaStream_t)stream>>>((const long long*)hist, *tab, iou, iou_stride,
-                                                                      miou);
+  int cmax = 0;
+  for (int i = 0; i < tab->n_datasets; ++i) cmax = tab->C[i] > cmax ? tab->C[i] : cmax;
+  MDSEG_REQUIRE((size_t)cmax * 16 <= 48 * 1024, "mdseg_miou_images: more than 3072 classes");
+  miou_images_kernel<<<tab->n_datasets, 256, (size_t)cmax * 16, (cudaStream_t)stream>>>((const long long*)hist, *tab,
+                                                                                       iou, iou_stride, miou);
   MDSEG_LAUNCH_OK();
   return 0;
 }

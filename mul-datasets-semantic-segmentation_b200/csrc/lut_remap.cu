@@ -109,6 +109,104 @@ __global__ void __launch_bounds__(256) lut_remap_kernel(const In* __restrict__ i
   }
 }
 
+// Coalesced on BOTH sides for any (In, Out) width pair: a warp owns a tile of 512 consecutive pixels,
+// loads it with 16-byte vectors in the input's own coalesced order, looks the bytes up and parks them in a
+// 512-byte shared-memory tile, then re-reads that tile in the output's coalesced order and stores 16-byte
+// vectors.  (The thread-contiguous variant above writes 128-byte runs per thread when widening u8 -> i64:
+// every store instruction touches 32 different lines.)
+template <typename T> struct Lane16 {           // pixels one lane moves per 16-byte vector
+  static constexpr int kPx = 16 / (int)sizeof(T);
+};
+template <typename In> __device__ __forceinline__ int in_value(const int4& v, int i);
+template <> __device__ __forceinline__ int in_value<uint8_t>(const int4& v, int i) {
+  const uint32_t w = i < 4 ? (uint32_t)v.x : i < 8 ? (uint32_t)v.y : i < 12 ? (uint32_t)v.z : (uint32_t)v.w;
+  return (int)((w >> (8 * (i & 3))) & 0xffu);
+}
+template <> __device__ __forceinline__ int in_value<int32_t>(const int4& v, int i) {
+  const int a = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+  return ((unsigned)a < 256u) ? a : -1;
+}
+template <> __device__ __forceinline__ int in_value<int64_t>(const int4& v, int i) {
+  const int lo = i == 0 ? v.x : v.z, hi = i == 0 ? v.y : v.w;
+  return (hi == 0 && (unsigned)lo < 256u) ? lo : -1;
+}
+template <typename Out> __device__ __forceinline__ int4 out_pack(const uint8_t* t);  // t: Lane16<Out>::kPx bytes
+template <> __device__ __forceinline__ int4 out_pack<uint8_t>(const uint8_t* t) {
+  return *reinterpret_cast<const int4*>(t);
+}
+template <> __device__ __forceinline__ int4 out_pack<int32_t>(const uint8_t* t) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(t);
+  return make_int4((int)(w & 0xff), (int)((w >> 8) & 0xff), (int)((w >> 16) & 0xff), (int)(w >> 24));
+}
+template <> __device__ __forceinline__ int4 out_pack<int64_t>(const uint8_t* t) {
+  const uint32_t w = *reinterpret_cast<const uint16_t*>(t);
+  return make_int4((int)(w & 0xff), 0, (int)(w >> 8), 0);
+}
+
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) lut_remap_tile_kernel(const In* __restrict__ in, Out* __restrict__ out,
+                                                            const uint8_t* __restrict__ lut, int oob, int64_t n,
+                                                            const int32_t* __restrict__ lut_ids, int n_luts,
+                                                            int* err_flag) {
+  constexpr int kTile = 512;
+  __shared__ uint8_t s_lut[256];
+  __shared__ __align__(16) uint8_t s_tile[8][kTile];
+  {
+    const int id = lut_ids ? lut_ids[blockIdx.y] : 0;
+    const bool ok = id >= 0 && id < n_luts;
+    s_lut[threadIdx.x] = ok ? lut[(int64_t)id * 256 + threadIdx.x] : (uint8_t)oob;
+    if (!ok && threadIdx.x == 0 && blockIdx.x == 0 && err_flag) atomicOr(err_flag, MDSEG_ERR_DATASET_ID);
+    in += (int64_t)blockIdx.y * n;
+    out += (int64_t)blockIdx.y * n;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* tile = s_tile[warp];
+  constexpr int kIn = Lane16<In>::kPx, kOut = Lane16<Out>::kPx;
+  constexpr int kInIt = kTile / (32 * kIn), kOutIt = kTile / (32 * kOut);
+  const int64_t n_tiles = n / kTile;
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < n_tiles; t += wstride) {
+    const In* src = in + t * kTile;
+    int4 v[kInIt];
+#pragma unroll
+    for (int j = 0; j < kInIt; ++j) v[j] = ldg_stream_v4(src + (j * 32 + lane) * kIn);
+#pragma unroll
+    for (int j = 0; j < kInIt; ++j) {
+      uint8_t o[kIn];
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) {
+        const int x = in_value<In>(v[j], i);
+        o[i] = (uint8_t)((x >= 0) ? (int)s_lut[x] : oob);
+      }
+      uint8_t* dst = tile + (j * 32 + lane) * kIn;
+      if (kIn == 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          w[q] = o[4 * q] | ((uint32_t)o[4 * q + 1] << 8) | ((uint32_t)o[4 * q + 2] << 16) | ((uint32_t)o[4 * q + 3] << 24);
+        *reinterpret_cast<int4*>(dst) = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+      } else if (kIn == 4) {
+        *reinterpret_cast<uint32_t*>(dst) = o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+      } else {
+        *reinterpret_cast<uint16_t*>(dst) = (uint16_t)(o[0] | ((uint16_t)o[1] << 8));
+      }
+    }
+    __syncwarp();
+    Out* dstg = out + t * kTile;
+#pragma unroll
+    for (int j = 0; j < kOutIt; ++j)
+      stg_stream_v4(dstg + (j * 32 + lane) * kOut, out_pack<Out>(tile + (j * 32 + lane) * kOut));
+    __syncwarp();
+  }
+  // ragged tail (< 512 elements)
+  for (int64_t i = n_tiles * kTile + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    long long xv = (long long)in[i];
+    out[i] = (Out)((xv >= 0 && xv < 256) ? (int)s_lut[xv] : oob);
+  }
+}
+
 // Unaligned fallback: one element per thread.
 template <typename In, typename Out>
 __global__ void __launch_bounds__(256) lut_remap_scalar_kernel(const In* __restrict__ in, Out* __restrict__ out,
@@ -145,8 +243,12 @@ int launch(const void* in, void* out, const uint8_t* lut, int oob, int64_t n, cu
     int64_t blocks = ceil_div64(nvec > 0 ? nvec : 1, 256);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    lut_remap_kernel<In, Out><<<dim3((unsigned)blocks, (unsigned)n_images), 256, 0, st>>>(
-        (const In*)in, (Out*)out, lut, oob, n, lut_ids, n_luts, err_flag);
+    if (sizeof(In) != sizeof(Out))  // widening / narrowing: the tile kernel keeps both sides coalesced
+      lut_remap_tile_kernel<In, Out><<<dim3((unsigned)blocks, (unsigned)n_images), 256, 0, st>>>(
+          (const In*)in, (Out*)out, lut, oob, n, lut_ids, n_luts, err_flag);
+    else
+      lut_remap_kernel<In, Out><<<dim3((unsigned)blocks, (unsigned)n_images), 256, 0, st>>>(
+          (const In*)in, (Out*)out, lut, oob, n, lut_ids, n_luts, err_flag);
   } else {
     int64_t blocks = ceil_div64(n, 256);
     if (blocks > cap) blocks = cap;
