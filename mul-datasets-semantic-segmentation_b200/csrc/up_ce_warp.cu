@@ -224,7 +224,7 @@ constexpr size_t kOffBars = kOffRb + 2 * kSpan * 4;
 constexpr size_t kSmem = kOffBars + (kStages + 1) * 8;
 static_assert(kOffCm % 128 == 0 && kOffLab % 16 == 0 && kOffRb % 16 == 0 && kOffBars % 8 == 0, "smem carve-up");
 
-__global__ void __launch_bounds__(32, 12) up_ce_fwd_warp_kernel(const __grid_constant__ Maps maps,
+__global__ void __launch_bounds__(32, 14) up_ce_fwd_warp_kernel(const __grid_constant__ Maps maps,
                                                                 const __grid_constant__ CUtensorMap cmap,
                                                                 const __grid_constant__ Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
