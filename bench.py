@@ -256,7 +256,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     gpu_launches = launches["n"]
-    clk = clocks.summary() if clocks else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +293,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = px * world / (float(t.item()) / e2e_steps * 1e-3)
+    clk = clocks.summary() if clocks else None  # sampled over the device-resident and the end-to-end timed loops
     del h_x, d_x
 
     # ---- per-kernel durations (separate loop, L2 flushed between launches) -> roofline -------------------
@@ -347,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
             traffic = None
             prof = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(prof):
-                traffic = json.load(open(prof)).get(top)
+                traffic = json.load(open(prof)).get(top)  # ncu dram bytes of the call's dominant kernel
             roof = {"kernel": top, "bound": "hbm", "achieved": cand[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": cand[top]["frac"], "traffic": traffic, "peak_source": peak_src,
                     "duration_ms": cand[top]["ms_per_step"]}
