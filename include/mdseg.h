@@ -314,6 +314,19 @@ int mdseg_mds_bwd(const mdseg_src_table* src /*host*/, const mdseg_graph_table* 
                   const float* grad_out, float grad_scale, void* dx, int dx_dtype, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* The same backward without a projection (aux heads, loss_cross_datasets.py:1044-1056): the gradient w.r.t.
+ * the low-res sources, written into `dst` (base / image_stride / C per dataset as in `src`, any float
+ * dtype).  Only the images of dataset d are written in dst->base[d]; the caller zero-initialises the rest
+ * (the reference row-selects aux_logits[i][dataset_ids == i], so those rows get no gradient).
+ * Sources must be fp32 on the fused route; other cases take the two-plane route inside the workspace. */
+size_t mdseg_up_ce_bwd_direct_workspace_bytes(const mdseg_src_table* src /*host*/, int n_images, int h, int w, int H,
+                                              int W);
+int mdseg_up_ce_bwd_direct(const mdseg_src_table* src /*host*/, const int32_t* dataset_ids, const void* labels,
+                           int label_dtype, int n_images, int h, int w, int H, int W, int ignore,
+                           const float* loss_px, const float* lse_px, mdseg_ohem_state* states,
+                           const float* grad_out, float grad_scale, const mdseg_src_table* dst /*host*/,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* out = a + b converted to out_dtype (aux heads: dlogits_aux = A + B) */
 int mdseg_add_planes(const float* a, const float* b, void* out, int out_dtype,
                      int64_t n, void* stream);

@@ -689,3 +689,100 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
   }
   return 2;
 }
+
+// ---- the same kernel without a projection: aux heads (a10) and any direct upsample + CE --------------------
+extern "C" size_t mdseg_up_ce_bwd_direct_workspace_bytes(const mdseg_src_table* src, int n_images, int h, int w, int H,
+                                                         int W) {
+  using namespace mdseg;
+  if (!src || src->n_datasets <= 0 || src->n_datasets > MDSEG_MAX_DATASETS || n_images <= 0 || h <= 0 || w <= 0 ||
+      H <= 0 || W <= 0)
+    return 256;
+  const Geom gm = geom_of(h, w, H, W);
+  const int c_max = src_max_c(src);
+  if (gm.W % 16 == 0 && tma::fast_geometry(*src, gm)) {
+    const int sr = pick_seg_rows(h);
+    const int n_seg = (h - 1 + sr - 1) / sr;
+    return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W * 5 + 1024;
+  }
+  size_t planes = 0;  // generic route: two fp32 planes per dataset, [n_images, C_d, h, w] each
+  for (int i = 0; i < src->n_datasets; ++i) planes += 2 * (size_t)n_images * src->C[i] * h * w * 4;
+  return planes + 256;
+}
+
+extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t* dataset_ids, const void* labels,
+                                      int label_dtype, int n_images, int h, int w, int H, int W, int ignore,
+                                      const float* loss_px, const float* lse_px, mdseg_ohem_state* states,
+                                      const float* grad_out, float grad_scale, const mdseg_src_table* dst,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(src && dst && src->n_datasets > 0 && src->n_datasets <= MDSEG_MAX_DATASETS &&
+                    dst->n_datasets == src->n_datasets && is_float_dtype(dst->dtype),
+                "mdseg_up_ce_bwd_direct: bad source / destination table");
+  for (int i = 0; i < src->n_datasets; ++i)
+    MDSEG_REQUIRE(dst->base[i] && dst->C[i] == src->C[i], "mdseg_up_ce_bwd_direct: destination %d does not match", i);
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0 && H > 0 && W > 0 && h <= 65535,
+                "mdseg_up_ce_bwd_direct: bad shape");
+  if (n_images == 0) return 0;
+  MDSEG_REQUIRE(labels && loss_px && lse_px && states && workspace, "mdseg_up_ce_bwd_direct: null pointer");
+  MDSEG_REQUIRE(workspace_bytes >= mdseg_up_ce_bwd_direct_workspace_bytes(src, n_images, h, w, H, W),
+                "mdseg_up_ce_bwd_direct: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t hw = (int64_t)h * w;
+  const int c_max = src_max_c(src);
+  const Geom gm = geom_of(h, w, H, W);
+  float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+
+  if (!(gm.W % 16 == 0 && tma::fast_geometry(*src, gm))) {
+    // generic route: two planes per dataset (zero for the images of other datasets), then their sum
+    mdseg_src_table dA = *src, dB = *src;
+    dA.dtype = MDSEG_F32; dB.dtype = MDSEG_F32; dA.cmax = nullptr; dB.cmax = nullptr;
+    size_t off = 0;
+    for (int i = 0; i < src->n_datasets; ++i) {
+      const size_t n = (size_t)n_images * src->C[i] * hw;
+      dA.base[i] = ws + off; dB.base[i] = ws + off + n;
+      dA.image_stride[i] = (long long)src->C[i] * hw; dB.image_stride[i] = dA.image_stride[i];
+      dA.C_alloc[i] = src->C[i]; dB.C_alloc[i] = src->C[i];
+      off += 2 * n;
+    }
+    MDSEG_CUDA_OK(cudaMemsetAsync(ws, 0, off * 4, s));
+    if (int rc = mdseg_up_ce_bwd(src, dataset_ids, labels, label_dtype, n_images, h, w, H, W, ignore, loss_px, lse_px,
+                                 states, grad_out, grad_scale, &dA, &dB, stream))
+      return rc;
+    for (int i = 0; i < src->n_datasets; ++i) {
+      MDSEG_REQUIRE(dst->image_stride[i] == (long long)src->C[i] * hw,
+                    "mdseg_up_ce_bwd_direct: the generic route needs dense [n_images, C, h, w] destinations");
+      if (int rc = mdseg_add_planes((const float*)dA.base[i], (const float*)dB.base[i], const_cast<void*>(dst->base[i]),
+                                    dst->dtype, (int64_t)n_images * src->C[i] * hw, stream))
+        return rc;
+    }
+    return 0;
+  }
+
+  Args a;
+  a.src = *src; a.src_scaled = 0; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
+  a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
+  for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
+    const bool on = i < src->n_datasets;
+    a.out_base[i] = on ? const_cast<void*>(dst->base[i]) : nullptr;
+    a.out_image_stride[i] = on ? dst->image_stride[i] : 0;
+    a.out_channels[i] = on ? src->C[i] : 0;
+    a.g[i] = GraphDev{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // identity: channel = class
+  }
+  a.zero_invalid = 0;  // rows of images that do not belong to a head stay as the caller initialised them
+  a.seg_rows = pick_seg_rows(h);
+  a.n_seg = (h - 1 + a.seg_rows - 1) / a.seg_rows;
+  a.n_strips = (w + kOwn - 1) / kOwn;
+  a.c_scr = c_max;
+  a.scrA = ws;
+  a.scrB = ws + (size_t)n_images * a.n_seg * c_max * w;
+  a.lw2 = a.scrB + (size_t)n_images * a.n_seg * c_max * w;
+  a.sel8 = reinterpret_cast<uint8_t*>(a.lw2 + (size_t)n_images * H * W);
+  tma::Maps maps;
+  if (int rc = tma::make_maps(a.src, gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
+  switch (dst->dtype) {
+    case MDSEG_F32: return launch<float>(label_dtype, maps, a, n_images, c_max, s);
+    case MDSEG_BF16: return launch<__nv_bfloat16>(label_dtype, maps, a, n_images, c_max, s);
+    case MDSEG_F16: return launch<__half>(label_dtype, maps, a, n_images, c_max, s);
+  }
+  return 2;
+}

@@ -42,6 +42,37 @@ int max_cell_population(float scale, int n_in, int n_out) {
 
 }  // namespace
 
+namespace {
+// channel maximum of the low-res sources: cmax[b, y, x] = max_c src[b, c, y, x]
+__global__ void __launch_bounds__(256)
+channel_max_kernel(const mdseg_src_table src, const int32_t* __restrict__ dataset_ids, int64_t hw) {
+  const int b = blockIdx.y;
+  const int d = dataset_ids ? dataset_ids[b] : 0;
+  if (d < 0 || d >= src.n_datasets) return;
+  const float* img = (const float*)src.base[d] + (int64_t)b * src.image_stride[d];
+  const int C = src.C[d];
+  float* out = src.cmax + (int64_t)b * hw;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < hw / 4; q += (int64_t)gridDim.x * blockDim.x) {
+    float4 m = *reinterpret_cast<const float4*>(img + q * 4);
+    for (int c = 1; c < C; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(img + (int64_t)c * hw + q * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    *reinterpret_cast<float4*>(out + q * 4) = m;
+  }
+}
+}  // namespace
+
+int channel_max(const mdseg_src_table& src, const int32_t* dataset_ids, int n_images, int64_t hw, cudaStream_t s) {
+  int64_t bx = ceil_div64(hw / 4, 256);
+  const int64_t want = ceil_div64((int64_t)sm_count() * 8, n_images);
+  if (bx > want) bx = want;
+  if (bx < 1) bx = 1;
+  channel_max_kernel<<<dim3((unsigned)bx, (unsigned)n_images), 256, 0, s>>>(src, dataset_ids, hw);
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+
 bool fast_geometry(const mdseg_src_table& src, const Geom& gm) {
   if (src.dtype != MDSEG_F32) return false;
   if (gm.h < 2 || gm.w < 2 || gm.w % 4 != 0) return false;

@@ -105,6 +105,8 @@ __device__ __forceinline__ void cell_span(const AxisMap& m, int c, int n_out, in
 
 // host: tensor maps over the fp32 sources [n_images][C_alloc][h][w] with box (box_w, box_h, box_c, 1)
 int make_maps(const mdseg_src_table& src, const Geom& gm, int n_images, int box_w, int box_h, int box_c, Maps* out);
+// cmax[b, y, x] = max_c src[b, c, y, x] for fp32 sources with hw % 4 == 0 (src.cmax is the output plane)
+int channel_max(const mdseg_src_table& src, const int32_t* dataset_ids, int n_images, int64_t hw, cudaStream_t s);
 // fast-path geometry: fp32 sources, 16-byte aligned rows, h,w >= 2, 1 <= up-sampling factor <= 5, C <= 254
 bool fast_geometry(const mdseg_src_table& src, const Geom& gm);
 

@@ -26,7 +26,7 @@
 #include <cuda.h>
 #include <float.h>
 
-#include "up_ce_internal.cuh"
+#include "tma_util.cuh"
 
 namespace mdseg {
 namespace {
@@ -321,25 +321,6 @@ up_ce_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const FwdArgs a) {
 #undef MDSEG_CASE
   if (err) atomicOr(a.err_flag, err);
   block_accumulate_stats(st_dev, st.n_valid, st.n_hard, (double)st.sum_hard, st.n_px);
-}
-
-// channel maximum of the low-res sources: cmax[b, y, x] = max_c src[b, c, y, x]
-__global__ void __launch_bounds__(256)
-channel_max_kernel(const mdseg_src_table src, const int32_t* __restrict__ dataset_ids, int64_t hw) {
-  const int b = blockIdx.y;
-  const int d = dataset_ids ? dataset_ids[b] : 0;
-  if (d < 0 || d >= src.n_datasets) return;
-  const float* img = (const float*)src.base[d] + (int64_t)b * src.image_stride[d];
-  const int C = src.C[d];
-  float* out = src.cmax + (int64_t)b * hw;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < hw / 4; q += (int64_t)gridDim.x * blockDim.x) {
-    float4 m = *reinterpret_cast<const float4*>(img + q * 4);
-    for (int c = 1; c < C; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(img + (int64_t)c * hw + q * 4);
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-    }
-    *reinterpret_cast<float4*>(out + q * 4) = m;
-  }
 }
 
 // =================================================================================================
@@ -679,14 +660,8 @@ int up_ce_fwd_tma(const FwdArgs& a, int label_dtype, int n_images, cudaStream_t 
   if (!tma_applicable(a.src, a.gm)) return -1;
   TmaMaps maps;
   if (int rc = make_maps(a.src, a.gm, n_images, &maps)) return rc;
-  if (!a.src.cmax_ready) {
-    const int64_t hw = (int64_t)a.gm.h * a.gm.w;
-    int64_t bx = ceil_div64(hw / 4, 256);
-    int64_t want = ceil_div64((int64_t)sm_count() * 8, n_images);
-    if (bx > want) bx = want;
-    channel_max_kernel<<<dim3((unsigned)bx, (unsigned)n_images), 256, 0, s>>>(a.src, a.dataset_ids, hw);
-    MDSEG_LAUNCH_OK();
-  }
+  if (!a.src.cmax_ready)
+    if (int rc = tma::channel_max(a.src, a.dataset_ids, n_images, (int64_t)a.gm.h * a.gm.w, s)) return rc;
   switch (label_dtype) {
     case MDSEG_U8: return launch_fwd<uint8_t>(maps, a, n_images, s);
     case MDSEG_I32: return launch_fwd<int32_t>(maps, a, n_images, s);

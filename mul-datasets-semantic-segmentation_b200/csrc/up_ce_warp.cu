@@ -362,12 +362,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // Return 0 = launched, -1 = not applicable (caller falls back), > 0 = error.
 int up_ce_fwd_warp(const FwdArgs& fa, int label_dtype, int n_images, cudaStream_t s) {
-  if (label_dtype != MDSEG_U8 || fa.src.cmax == nullptr || !fa.src.cmax_ready) return -1;
+  if (label_dtype != MDSEG_U8 || fa.src.cmax == nullptr) return -1;
   if (fa.gm.W % 16 != 0 || ((uintptr_t)fa.labels & 15) != 0 || ((uintptr_t)fa.src.cmax & 15) != 0) return -1;
   if (fa.ignore < 0 || fa.ignore > 255) return -1;
   if (!tma::fast_geometry(fa.src, fa.gm)) return -1;
   tma::Maps maps;
   if (int rc = tma::make_maps(fa.src, fa.gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
+  if (!fa.src.cmax_ready)  // aux heads: nobody produced the channel maximum yet
+    if (int rc = tma::channel_max(fa.src, fa.dataset_ids, n_images, (int64_t)fa.gm.h * fa.gm.w, s)) return rc;
   CUtensorMap cmap;
   {
     void* p = nullptr;

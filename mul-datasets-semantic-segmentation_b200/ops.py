@@ -603,6 +603,7 @@ class _UpOhemCE(torch.autograd.Function):
     def forward(ctx, labels, dataset_ids, thresh, ignore, seg_per_dataset, *srcs):
         labels = _labels(labels)
         _require_cuda(labels, *srcs)
+        labels = _compact_labels(labels, max(s.shape[1] for s in srcs), ignore)
         B, H, W = labels.shape
         dev = labels.device
         n = len(srcs)
@@ -642,18 +643,14 @@ class _UpOhemCE(torch.autograd.Function):
         scratch = torch.empty(1, dtype=torch.float32, device=labels.device) if dt == torch.float32 else None
         src = _src_table([s.data_ptr() for s in srcs], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset,
                          cmax=scratch, cmax_ready=True)
-        # images of other datasets get a zero gradient (their rows are never selected, :1051)
-        dAs = [torch.zeros(s.shape, dtype=torch.float32, device=s.device) for s in srcs]
-        dBs = [torch.zeros(s.shape, dtype=torch.float32, device=s.device) for s in srcs]
-        dA = _src_table([t.data_ptr() for t in dAs], [c * h * w for c in Cs], Cs, N.F32, seg_per_dataset)
-        dB = _src_table([t.data_ptr() for t in dBs], [c * h * w for c in Cs], Cs, N.F32, seg_per_dataset)
-        N.call("mdseg_up_ce_bwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, ignore,
-               _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dA), C.byref(dB), _stream())
-        grads = []
-        for s, a, b in zip(srcs, dAs, dBs):
-            o = torch.empty_like(s)
-            N.call("mdseg_add_planes", _ptr(a), _ptr(b), _ptr(o), _DT[dt], a.numel(), _stream())
-            grads.append(o)
+        # images of other datasets get a zero gradient (their rows are never selected, :1051): zero-initialised
+        # outputs, the kernel writes only the rows of a head's own images
+        grads = [torch.zeros_like(s) for s in srcs]
+        dst = _src_table([t.data_ptr() for t in grads], [c * h * w for c in Cs], Cs, _DT[dt], seg_per_dataset)
+        nbytes = N.lib.mdseg_up_ce_bwd_direct_workspace_bytes(C.byref(src), B, h, w, H, W)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=labels.device)
+        N.call("mdseg_up_ce_bwd_direct", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W,
+               ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dst), _ptr(ws), nbytes, _stream())
         return (None, None, None, None, None, *grads)
 
 

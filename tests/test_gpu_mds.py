@@ -231,3 +231,33 @@ def test_projection_alone_matches_einsum(ops):
     for b, d in enumerate(ids):
         want = tr.project(x[b:b + 1], graphs[d])[0]
         assert torch.equal(y[b, :n_cats[d]].cpu(), want)  # 0/1 graphs: exact
+
+
+@pytest.mark.parametrize("geom", [(16, 32, 64, 128), (9, 12, 36, 48), (7, 9, 25, 33)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_aux_heads_per_dataset_selection(ops, geom, dt):
+    """Per-dataset aux heads (loss_cross_datasets.py:1044-1056): one OHEM selection per dataset, rows of other
+    datasets' images get a zero gradient.  The first geometry takes the fused warp-private kernels (uint8 staged
+    labels, direct backward), the others the general route."""
+    h, w, H, W = geom
+    n_cats, ids = [5, 3, 7], [2, 0, 1, 2, 0, 1]
+    B = len(ids)
+    g = torch.Generator().manual_seed(h * 17 + W)
+    aux = [(torch.randn(B, c, h, w, generator=g) * 2.0).to(dt) for c in n_cats]
+    labels = torch.stack([torch.randint(0, n_cats[d], (H, W), generator=g) for d in ids])
+    labels[torch.rand(B, H, W, generator=g) < 0.05] = 255
+    thresh = ops.neg_log(0.7)
+    auxd = [a.to(DEV).requires_grad_(True) for a in aux]
+    per_ds = ops.up_ohem_ce(auxd, labels.to(DEV), torch.tensor(ids, device=DEV), thresh, seg_per_dataset=True)
+    (per_ds * torch.tensor([1.0, 2.0, 0.5], device=DEV)).sum().backward()
+    ops.check_errors(DEV)
+    tol = RTOL32 if dt == torch.float32 else 2e-2
+    ids_np = np.array(ids)
+    for d, c in enumerate(n_cats):
+        sel = ids_np == d
+        ref_loss, ref_dsrc, _, _ = f64.up_ohem_ce(aux[d].float().numpy()[sel], labels.numpy()[sel], thresh)
+        assert abs(float(per_ds[d]) - ref_loss) <= tol * abs(ref_loss), d
+        got = auxd[d].grad.float().cpu().numpy()
+        scale = [1.0, 2.0, 0.5][d]
+        assert rel_err(got[sel], scale * ref_dsrc) <= tol, d
+        assert not got[~sel].any(), d
