@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--label-dtype", default="int64", choices=["int64", "uint8"],
                     help="dtype of the remapped label maps (the reference's loaders hand int64 to the loss)")
+    ap.add_argument("--with-aux", action="store_true",
+                    help="add the per-dataset aux heads (OhemCELoss 0.7 on aux_logits[i], weight 0.2; "
+                         "loss_cross_datasets.py:1044-1056,1129-1130) to the step; not part of the headline config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
     return ap.parse_args()
@@ -157,7 +160,8 @@ class Clocks(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL = {"mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
+KERNELS_PER_CALL = {"mdseg_up_ce_bwd_direct": 3,
+                    "mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
                     "mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
                     "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
                     "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 2, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
@@ -197,6 +201,10 @@ def run_ours(args, rank, world, local_rank):
     ids_t = torch.tensor(ids, dtype=torch.int32, device=dev)
     slices = dataset_slices(ids)
     thresh = ops.neg_log(0.4)
+    aux = None
+    if args.with_aux:
+        agen = torch.Generator(device=dev).manual_seed(99 + rank)
+        aux = [torch.randn(B, c, bt["h"], bt["w"], generator=agen, device=dev).requires_grad_(True) for c in n_cats]
     x = bt["x"].requires_grad_(True)
     offs = np.cumsum([0] + [c * c for c in n_cats])
     hist_flat = torch.zeros(int(offs[-1]), dtype=torch.int64, device=dev)
@@ -224,6 +232,11 @@ def run_ours(args, rank, world, local_rank):
         # a5-a9: fused projection + upsample + OhemCE fwd, selection, bwd
         xin.grad = None
         loss = ops.mds_proj_ohem_ce(xin, labels, ids_t, graphs, thresh)
+        if aux is not None:
+            for t in aux:
+                t.grad = None
+            per_ds = ops.up_ohem_ce(aux, labels, ids_t, ops.neg_log(0.7), seg_per_dataset=True)
+            loss = loss + 0.2 * torch.nan_to_num(per_ds, nan=0.0).sum()
         loss.backward()
         if overlap:
             main.wait_stream(side)
@@ -371,6 +384,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD_NAMES[args.workload], "name": args.workload,
                        "pixels_per_step_per_gpu": px, "labels": args.label_dtype, "logits": "f32 NCHW",
                        "bi_graphs": "0/1 column-one-hot (SEG stage)", "ohem_thresh": 0.4,
+                       "aux_heads": bool(args.with_aux),
                        "l2": "inputs_exceed_l2 (logits %.2f GB, labels+preds %.2f GB per step)" %
                              (bt["x"].numel() * 4 / 1e9, px * (1 + (8 if lab_dt == torch.int64 else 1) + 8) / 1e9),
                        "parallelism": f"dp{world} (images sharded, OHEM selection rank-local, one int64 hist all-reduce)",
