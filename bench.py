@@ -56,6 +56,12 @@ def parse():
     ap.add_argument("--with-aux", action="store_true",
                     help="add the per-dataset aux heads (OhemCELoss 0.7 on aux_logits[i], weight 0.2; "
                          "loss_cross_datasets.py:1044-1056,1129-1130) to the step; not part of the headline config")
+    ap.add_argument("--logits-dtype", default="f32", choices=["f32", "bf16", "f16"],
+                    help="dtype of logits_uni / dlogits_uni (AMP trainers hand fp16 logits to the loss; the CE "
+                         "arithmetic stays fp32 either way).  The headline is f32.")
+    ap.add_argument("--eager-gpu", action="store_true",
+                    help="also time the reference's own torch op sequence (oracle/torch_ref.py, the same code as the "
+                         "CPU baseline) on CUDA tensors on this GPU: PyTorch eager, reported as 'reference_eager_gpu'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
     return ap.parse_args()
@@ -205,6 +211,8 @@ def run_ours(args, rank, world, local_rank):
     if args.with_aux:
         agen = torch.Generator(device=dev).manual_seed(99 + rank)
         aux = [torch.randn(B, c, bt["h"], bt["w"], generator=agen, device=dev).requires_grad_(True) for c in n_cats]
+    ldt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.logits_dtype]
+    bt["x"] = bt["x"].to(ldt)
     x = bt["x"].requires_grad_(True)
     offs = np.cumsum([0] + [c * c for c in n_cats])
     hist_flat = torch.zeros(int(offs[-1]), dtype=torch.int64, device=dev)
@@ -382,11 +390,12 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[args.workload], "name": args.workload,
-                       "pixels_per_step_per_gpu": px, "labels": args.label_dtype, "logits": "f32 NCHW",
+                       "pixels_per_step_per_gpu": px, "labels": args.label_dtype,
+                       "logits": f"{args.logits_dtype} NCHW (CE arithmetic fp32)",
                        "bi_graphs": "0/1 column-one-hot (SEG stage)", "ohem_thresh": 0.4,
                        "aux_heads": bool(args.with_aux),
                        "l2": "inputs_exceed_l2 (logits %.2f GB, labels+preds %.2f GB per step)" %
-                             (bt["x"].numel() * 4 / 1e9, px * (1 + (8 if lab_dt == torch.int64 else 1) + 8) / 1e9),
+                             (bt["x"].numel() * bt["x"].element_size() / 1e9, px * (1 + (8 if lab_dt == torch.int64 else 1) + 8) / 1e9),
                        "parallelism": f"dp{world} (images sharded, OHEM selection rank-local, one int64 hist all-reduce)",
                        "streams": "loss fwd/select/bwd on the main stream, confusion matrices + all-reduce + mIoU on a side stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -416,6 +425,48 @@ def cpu_step(bt):
         h = ls.confusion(labels[s:e].numpy(), bt["pred"][s:e].numpy(), bt["n_cats"][d])
         mious.append(ls.ious_miou(h)[1])
     return float(loss), mious
+
+
+def run_eager_gpu(args, local_rank):
+    """Context number: the reference's torch ops on the same B200, full batch, device-resident."""
+    dev = torch.device(f"cuda:{local_rank}")
+    bt = make_batch(args.workload, dev, 1234)
+    bt["graphs"] = [g.to(dev) for g in bt["graphs"]]
+    luts = [torch.from_numpy(l).to(dev) for l in bt["luts"]]
+    ids = bt["ids"]
+    ids_t = torch.tensor(ids, dtype=torch.int32, device=dev)
+    from oracle import torch_ref as tr
+
+    def step():
+        labels = torch.empty(bt["raw"].shape, dtype=torch.int64, device=dev)
+        for d, s, e in dataset_slices(ids):
+            labels[s:e] = luts[d][bt["raw"][s:e].long()].long()
+        x = bt["x"].detach().requires_grad_(True)
+        loss = tr.multi_dataset_seg_loss(x, labels, ids_t, bt["graphs"], 0.4)
+        loss.backward()
+        mious = []
+        for d, s, e in dataset_slices(ids):
+            c = bt["n_cats"][d]
+            keep = labels[s:e] != 255
+            h = torch.bincount(labels[s:e][keep] * c + bt["pred"][s:e][keep], minlength=c * c).view(c, c).double()
+            iou = h.diag() / (h.sum(0) + h.sum(1) - h.diag())
+            mious.append(torch.nanmean(iou))
+        return loss.detach(), torch.stack(mious)
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    px = len(ids) * bt["H"] * bt["W"]
+    return {"value": px / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "loss": float(out[0]),
+            "what": "oracle/torch_ref.py (einsum -> F.interpolate -> CrossEntropyLoss(none) -> OHEM) + torch.bincount, "
+                    "PyTorch eager on this GPU, device-resident inputs"}
 
 
 def cpu_sample_images(workload):
@@ -474,6 +525,9 @@ def main():
             res["cpu_baseline"] = cb
         else:
             res["cpu_baseline"] = None
+        if args.eager_gpu and world == 1:
+            torch.cuda.empty_cache()
+            res["reference_eager_gpu"] = run_eager_gpu(args, local_rank)
         print(json.dumps(res))
     if world > 1:
         dist.barrier()
