@@ -17,43 +17,52 @@
 namespace mdseg {
 namespace {
 
-constexpr int kPx = 8;  // pixels per thread per iteration
+// ---- coalesced warp-chunk loads ---------------------------------------------------------------------------
+// A warp walks "chunks" of 32 * kPL consecutive pixels: lane i holds the kPL consecutive pixels starting at
+// 32 * kPL * chunk + kPL * i, where kPL * max(sizeof(L), sizeof(P)) = 16 bytes, so every warp-level load is one
+// contiguous 512-byte (or narrower) request and each 32-byte sector crosses the L2 -> SM fabric exactly once.
+template <typename L, typename P> struct ChunkOf {
+  static constexpr int kPL = 16 / (int)(sizeof(L) > sizeof(P) ? sizeof(L) : sizeof(P));
+  static constexpr int kUnroll = kPL >= 16 ? 2 : 4;  // chunks in flight per warp
+};
 
-// load 8 consecutive labels/preds as ints; out-of-int-range values become -1
-template <typename T> struct Load8;
-template <> struct Load8<uint8_t> {
-  static __device__ __forceinline__ void load(const uint8_t* p, int (&x)[kPx]) {
-    int2 r = ldg_stream_v2(p);
-    const uint32_t w[2] = {(uint32_t)r.x, (uint32_t)r.y};
-#pragma unroll
-    for (int i = 0; i < kPx; ++i) x[i] = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
-  }
-};
-template <> struct Load8<int32_t> {
-  static __device__ __forceinline__ void load(const int32_t* p, int (&x)[kPx]) {
-    int4 a = ldg_stream_v4(p), b = ldg_stream_v4(p + 4);
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-  }
-};
-template <> struct Load8<int64_t> {
-  static __device__ __forceinline__ void load(const int64_t* p, int (&x)[kPx]) {
-    int4 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = ldg_stream_v4(p + 2 * j);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      x[2 * j + 0] = (v[j].y == 0) ? v[j].x : -1;
-      x[2 * j + 1] = (v[j].w == 0) ? v[j].z : -1;
+// N consecutive elements, kept as raw 32-bit words while the loads are in flight (N * sizeof(T) is 2, 4, 8 or
+// 16 bytes) and widened to ints on use; values outside [0, 2^31) become -1.
+template <typename T, int N> struct LoadPx {
+  static constexpr int kBytes = N * (int)sizeof(T);
+  static constexpr int kWords = kBytes < 4 ? 1 : kBytes / 4;
+  static_assert(kBytes == 2 || kBytes == 4 || kBytes == 8 || kBytes == 16, "unsupported vector width");
+  static __device__ __forceinline__ void load(const T* p, uint32_t (&w)[kWords]) {
+    if constexpr (kBytes == 16) {
+      const int4 r = ldg_stream_v4(p);
+      w[0] = (uint32_t)r.x; w[1] = (uint32_t)r.y; w[2] = (uint32_t)r.z; w[3] = (uint32_t)r.w;
+    } else if constexpr (kBytes == 8) {
+      const int2 r = ldg_stream_v2(p);
+      w[0] = (uint32_t)r.x; w[1] = (uint32_t)r.y;
+    } else if constexpr (kBytes == 4) {
+      asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+    } else {
+      unsigned short h;
+      asm volatile("ld.global.nc.L1::no_allocate.b16 %0, [%1];" : "=h"(h) : "l"(p));
+      w[0] = h;
     }
   }
+  static __device__ __forceinline__ int get(const uint32_t (&w)[kWords], int i) {
+    if constexpr (sizeof(T) == 1) return (int)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    else if constexpr (sizeof(T) == 4) return (int)w[i];
+    else return (w[2 * i + 1] == 0u) ? (int)w[2 * i] : -1;
+  }
 };
 
-template <bool kSmem>
-__device__ __forceinline__ void bump(unsigned* sh, unsigned long long* hist, int key, unsigned cnt) {
-  if (kSmem) atomicAdd(sh + key, cnt);
-  else atomicAdd(hist + key, (unsigned long long)cnt);
-}
+// where one CTA's counts go: a privatised shared-memory replica or, for histograms too large for it, HBM
+struct HistSink {
+  unsigned* sh;               // nullptr -> global
+  unsigned long long* glob;
+  __device__ __forceinline__ void add(int key, unsigned cnt) const {
+    if (sh) atomicAdd(sh + key, cnt);
+    else atomicAdd(glob + key, (unsigned long long)cnt);
+  }
+};
 
 // key of one pixel or -1 (ignored / invalid)
 __device__ __forceinline__ int make_key(int l, int p, const uint8_t* s_lut, bool has_lut, int Ca, int Cb, int ignore,
@@ -68,66 +77,119 @@ __device__ __forceinline__ int make_key(int l, int p, const uint8_t* s_lut, bool
   return l * Cb + p;
 }
 
-template <typename L, typename P, bool kSmem, bool kVec>
-__global__ void __launch_bounds__(256)
+// One chunk: run-length aggregation.  Segmentation maps are piecewise constant, so most lanes hold kPL equal
+// keys ("uniform" lanes) and most uniform lanes continue their left neighbour's run: the first lane of such a
+// run issues ONE atomic for the whole run (its length comes from a ballot of the run boundaries).  Lanes whose
+// pixels differ fall back to a private run-length walk.  The shared-memory atomic unit retires about one lane
+// every two cycles per SM, which is the floor for maps without any spatial coherence.
+template <int N>
+__device__ __forceinline__ void warp_chunk_bump(const int (&key)[N], int lane, const HistSink& sink) {
+  bool uniform = true;
+#pragma unroll
+  for (int i = 1; i < N; ++i) uniform &= (key[i] == key[0]);
+  const unsigned umask = __ballot_sync(0xffffffffu, uniform);
+  const int left = __shfl_up_sync(0xffffffffu, key[0], 1);
+  const bool left_uniform = lane > 0 && ((umask >> (lane - 1)) & 1u);
+  const bool head = uniform && !(left_uniform && left == key[0]);
+  const unsigned boundary = __ballot_sync(0xffffffffu, !uniform || head);
+  if (uniform) {
+    if (head && key[0] >= 0) {
+      const unsigned rest = (lane == 31) ? 0u : (boundary >> (lane + 1));
+      const int lanes = rest ? __ffs((int)rest) : (32 - lane);
+      sink.add(key[0], (unsigned)(lanes * N));
+    }
+  } else {
+    int prev = key[0];
+    unsigned cnt = 1;
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+      if (key[i] == prev) {
+        ++cnt;
+      } else {
+        if (prev >= 0) sink.add(prev, cnt);
+        prev = key[i];
+        cnt = 1;
+      }
+    }
+    if (prev >= 0) sink.add(prev, cnt);
+  }
+}
+
+// All pixels [0, n) of one slice, spread over `n_warps` warps of which this is number `gw`.  `aligned` = both
+// pointers are 16-byte aligned (the chunk path); otherwise every pixel is read on its own.
+template <typename L, typename P>
+__device__ __forceinline__ void accumulate_slice(const L* __restrict__ label, const P* __restrict__ pred, int64_t n,
+                                                 bool aligned, int64_t gw, int64_t n_warps, const uint8_t* s_lut,
+                                                 bool has_lut, int Ca, int Cb, int ignore, const HistSink& sink,
+                                                 int& err) {
+  constexpr int kPL = ChunkOf<L, P>::kPL;
+  constexpr int kU = ChunkOf<L, P>::kUnroll;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_chunks = aligned ? n / (32 * kPL) : 0;
+  for (int64_t c0 = gw * kU; c0 < n_chunks; c0 += n_warps * kU) {
+    uint32_t l[kU][LoadPx<L, kPL>::kWords], p[kU][LoadPx<P, kPL>::kWords];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (c0 + u < n_chunks) {
+        const int64_t at = (c0 + u) * (32 * kPL) + lane * kPL;
+        LoadPx<L, kPL>::load(label + at, l[u]);
+        LoadPx<P, kPL>::load(pred + at, p[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (c0 + u < n_chunks) {
+        int key[kPL];
+#pragma unroll
+        for (int i = 0; i < kPL; ++i)
+          key[i] = make_key(LoadPx<L, kPL>::get(l[u], i), LoadPx<P, kPL>::get(p[u], i), s_lut, has_lut, Ca, Cb, ignore, err);
+        warp_chunk_bump<kPL>(key, lane, sink);
+      }
+    }
+  }
+  // ragged tail (and the whole slice when unaligned): one pixel per thread
+  for (int64_t i = n_chunks * (32 * kPL) + gw * 32 + lane; i < n; i += n_warps * 32) {
+    const int key = make_key(load_label<L>(label, i), load_label<P>(pred, i), s_lut, has_lut, Ca, Cb, ignore, err);
+    if (key >= 0) sink.add(key, 1u);
+  }
+}
+
+constexpr int kConfThreads = 1024;
+
+// Zero `replicas` shared-memory copies of a `bins`-bin histogram / add them into the int64 histogram in HBM.
+__device__ __forceinline__ void sh_hist_zero(unsigned* sh, int words) {
+  for (int i = threadIdx.x; i < words; i += blockDim.x) sh[i] = 0u;
+}
+__device__ __forceinline__ void sh_hist_flush(const unsigned* sh, int bins, int replicas, unsigned long long* hist) {
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+    unsigned long long s = 0;
+    for (int r = 0; r < replicas; ++r) s += sh[r * bins + b];
+    if (s) atomicAdd(hist + b, s);
+  }
+}
+
+template <typename L, typename P>
+__global__ void __launch_bounds__(kConfThreads)
 confusion_kernel(const L* __restrict__ label, const P* __restrict__ pred, const uint8_t* __restrict__ lut,
                  unsigned long long* __restrict__ hist, int Ca, int Cb, int ignore, int64_t n, int* err_flag,
-                 int replicas) {
+                 int replicas, int aligned) {
   extern __shared__ unsigned sh_hist[];
   __shared__ uint8_t s_lut[256];
   const int bins = Ca * Cb;
   const bool has_lut = lut != nullptr;
-  if (has_lut) s_lut[threadIdx.x] = lut[threadIdx.x];
-  if (kSmem) {
-    for (int i = threadIdx.x; i < bins * replicas; i += blockDim.x) sh_hist[i] = 0u;
-  }
+  if (has_lut && threadIdx.x < 256) s_lut[threadIdx.x] = lut[threadIdx.x];
+  const bool use_smem = replicas > 0;
+  if (use_smem) sh_hist_zero(sh_hist, bins * replicas);
   __syncthreads();
-  unsigned* my = sh_hist + (kSmem ? ((threadIdx.x >> 5) % replicas) * bins : 0);
-
+  const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  HistSink sink{use_smem ? sh_hist + (warp % replicas) * bins : nullptr, hist};
   int err = 0;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
-  if (kVec) {
-    const int64_t nvec = n / kPx;
-    for (int64_t v = gtid; v < nvec; v += gstride) {
-      int l[kPx], p[kPx];
-      Load8<L>::load(label + v * kPx, l);
-      Load8<P>::load(pred + v * kPx, p);
-      int prev = -1;
-      unsigned cnt = 0;
-#pragma unroll
-      for (int i = 0; i < kPx; ++i) {
-        int key = make_key(l[i], p[i], s_lut, has_lut, Ca, Cb, ignore, err);
-        if (key == prev) {
-          ++cnt;
-        } else {
-          if (prev >= 0) bump<kSmem>(my, hist, prev, cnt);
-          prev = key;
-          cnt = 1;
-        }
-      }
-      if (prev >= 0) bump<kSmem>(my, hist, prev, cnt);
-    }
-    const int64_t t = nvec * kPx + gtid;  // ragged tail (< 8 px)
-    if (t < n) {
-      int key = make_key(load_label<L>(label, t), load_label<P>(pred, t), s_lut, has_lut, Ca, Cb, ignore, err);
-      if (key >= 0) bump<kSmem>(my, hist, key, 1u);
-    }
-  } else {
-    for (int64_t i = gtid; i < n; i += gstride) {
-      int key = make_key(load_label<L>(label, i), load_label<P>(pred, i), s_lut, has_lut, Ca, Cb, ignore, err);
-      if (key >= 0) bump<kSmem>(my, hist, key, 1u);
-    }
-  }
+  accumulate_slice<L, P>(label, pred, n, aligned != 0, (int64_t)blockIdx.x * warps + warp, (int64_t)gridDim.x * warps,
+                         s_lut, has_lut, Ca, Cb, ignore, sink, err);
   if (err) atomicOr(err_flag, err);
-
-  if (kSmem) {
+  if (use_smem) {
     __syncthreads();
-    for (int b = threadIdx.x; b < bins; b += blockDim.x) {
-      unsigned long long s = 0;
-      for (int r = 0; r < replicas; ++r) s += sh_hist[r * bins + b];
-      if (s) atomicAdd(hist + b, s);
-    }
+    sh_hist_flush(sh_hist, bins, replicas, hist);
   }
 }
 
@@ -135,7 +197,7 @@ confusion_kernel(const L* __restrict__ label, const P* __restrict__ pred, const 
 // blockIdx.y = image b; d = dataset_ids[b] selects the LUT (luts + 256*d), the class count C[d] and the
 // square histogram hist + offset[d].  Shared-memory privatisation is decided per CTA from C[d].
 template <typename L, typename P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kConfThreads)
 confusion_images_kernel(const L* __restrict__ label, const P* __restrict__ pred, const uint8_t* __restrict__ luts,
                         const int32_t* __restrict__ dataset_ids, int64_t px_per_image,
                         unsigned long long* __restrict__ hist, const mdseg_hist_table tab, int ignore,
@@ -152,50 +214,26 @@ confusion_images_kernel(const L* __restrict__ label, const P* __restrict__ pred,
   const int bins = C * C;
   unsigned long long* h = hist + tab.offset[d];
   const bool has_lut = luts != nullptr;
-  if (has_lut) s_lut[threadIdx.x] = luts[(int64_t)d * 256 + threadIdx.x];
+  if (has_lut && threadIdx.x < 256) s_lut[threadIdx.x] = luts[(int64_t)d * 256 + threadIdx.x];
   const bool use_smem = bins <= smem_words;
   int replicas = 1;
   if (use_smem) {
     replicas = smem_words / bins;
     if (replicas > 8) replicas = 8;
-    for (int i = threadIdx.x; i < bins * replicas; i += blockDim.x) sh_hist[i] = 0u;
+    sh_hist_zero(sh_hist, bins * replicas);
   }
   __syncthreads();
-  unsigned* my = sh_hist + (use_smem ? ((threadIdx.x >> 5) % replicas) * bins : 0);
-  label += (int64_t)b * px_per_image;
-  pred += (int64_t)b * px_per_image;
-
+  const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  HistSink sink{use_smem ? sh_hist + (warp % replicas) * bins : nullptr, h};
   int err = 0;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nvec = px_per_image / kPx;  // the host guarantees 16-byte aligned image slices
-  for (int64_t v = gtid; v < nvec; v += gstride) {
-    int l[kPx], p[kPx];
-    Load8<L>::load(label + v * kPx, l);
-    Load8<P>::load(pred + v * kPx, p);
-    int prev = -1;
-    unsigned cnt = 0;
-#pragma unroll
-    for (int i = 0; i < kPx; ++i) {
-      int key = make_key(l[i], p[i], s_lut, has_lut, C, C, ignore, err);
-      if (key == prev) {
-        ++cnt;
-      } else {
-        if (prev >= 0) { if (use_smem) atomicAdd(my + prev, cnt); else atomicAdd(h + prev, (unsigned long long)cnt); }
-        prev = key;
-        cnt = 1;
-      }
-    }
-    if (prev >= 0) { if (use_smem) atomicAdd(my + prev, cnt); else atomicAdd(h + prev, (unsigned long long)cnt); }
-  }
+  // the host guarantees 16-byte aligned image slices
+  accumulate_slice<L, P>(label + (int64_t)b * px_per_image, pred + (int64_t)b * px_per_image, px_per_image, true,
+                         (int64_t)blockIdx.x * warps + warp, (int64_t)gridDim.x * warps, s_lut, has_lut, C, C, ignore,
+                         sink, err);
   if (err) atomicOr(err_flag, err);
   if (use_smem) {
     __syncthreads();
-    for (int k = threadIdx.x; k < bins; k += blockDim.x) {
-      unsigned long long sum = 0;
-      for (int r = 0; r < replicas; ++r) sum += sh_hist[r * bins + k];
-      if (sum) atomicAdd(h + k, sum);
-    }
+    sh_hist_flush(sh_hist, bins, replicas, h);
   }
 }
 
@@ -252,26 +290,28 @@ __global__ void __launch_bounds__(256) miou_images_kernel(const long long* __res
   }
 }
 
+// Grid shape shared by both launchers: one 1024-thread CTA per SM (32 warps keep ~128 KB of loads in flight and
+// halve the number of per-CTA histogram flushes compared with two smaller CTAs), the images' CTA count rounded
+// DOWN so that the whole grid is resident at once (a second, nearly empty wave would double the run time).
 template <typename L, typename P>
 int launch_images(const void* label, const void* pred, const uint8_t* luts, const int32_t* ids, int n_images,
                   int64_t ppi, int64_t* hist, const mdseg_hist_table& tab, int ignore, int32_t* err_flag,
                   cudaStream_t st) {
   int cmax = 0;
   for (int i = 0; i < tab.n_datasets; ++i) cmax = tab.C[i] > cmax ? tab.C[i] : cmax;
-  // privatised histogram: up to 24 KB of replicas for small C, one replica up to 96 KB, global atomics beyond
+  // privatised histogram: up to 32 KB of replicas for small C, one replica up to 200 KB, global atomics beyond
   size_t smem = (size_t)cmax * cmax * 4;
-  if (smem < 24 * 1024) smem = 24 * 1024;
-  if (smem > 96 * 1024) smem = 24 * 1024;
+  if (smem < 32 * 1024) smem = 32 * 1024;
+  if (smem > 200 * 1024) smem = 32 * 1024;
   auto k = confusion_images_kernel<L, P>;
   if (smem > 48 * 1024) MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (per_sm > 8) per_sm = 8;
-  if (per_sm < 1) per_sm = 1;
-  int64_t blocks = ceil_div64(ceil_div64(ppi, kPx), 256);
-  const int64_t cap = ceil_div64((int64_t)sm_count() * per_sm, n_images);
+  int per_sm = smem <= 100 * 1024 ? 2 : 1;  // 2 x 1024 threads is the SM's thread limit
+  constexpr int kPxPerCtaIter = (kConfThreads / 32) * 32 * ChunkOf<L, P>::kPL * ChunkOf<L, P>::kUnroll;
+  int64_t blocks = ceil_div64(ppi, kPxPerCtaIter);
+  const int64_t cap = ((int64_t)sm_count() * per_sm) / n_images;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k<<<dim3((unsigned)blocks, (unsigned)n_images), 256, smem, st>>>(
+  k<<<dim3((unsigned)blocks, (unsigned)n_images), kConfThreads, smem, st>>>(
       (const L*)label, (const P*)pred, luts, ids, ppi, reinterpret_cast<unsigned long long*>(hist), tab, ignore,
       err_flag, (int)(smem / 4));
   MDSEG_LAUNCH_OK();
@@ -294,39 +334,28 @@ int dispatch_pred_images(const void* label, const void* pred, int pred_dtype, co
 template <typename L, typename P>
 int launch(const void* label, const void* pred, const uint8_t* lut, int64_t* hist, int Ca, int Cb, int ignore,
            int64_t n, int32_t* err_flag, cudaStream_t st) {
-  const int sms = sm_count();
   const int64_t bins = (int64_t)Ca * Cb;
-  const bool vec = (((uintptr_t)label | (uintptr_t)pred) & 15) == 0;
+  const bool aligned = (((uintptr_t)label | (uintptr_t)pred) & 15) == 0;
   const size_t kMaxSmem = 200 * 1024;
-  const bool use_smem = (size_t)bins * 4 <= kMaxSmem;
-  int replicas = 1;
+  int replicas = 0;  // 0: histogram too large for shared memory, global atomics
   size_t smem = 0;
-  int ctas_per_sm = 8;
-  if (use_smem) {
-    replicas = (int)((24 * 1024) / (bins * 4));
+  int per_sm = 2;
+  if ((size_t)bins * 4 <= kMaxSmem) {
+    replicas = (int)((32 * 1024) / (bins * 4));
     if (replicas > 8) replicas = 8;
     if (replicas < 1) replicas = 1;
     smem = (size_t)bins * 4 * replicas;
-    int fit = (int)((220 * 1024) / (smem + 1024));
-    if (fit < 1) fit = 1;
-    if (ctas_per_sm > fit) ctas_per_sm = fit;
+    if (smem > 100 * 1024) per_sm = 1;
   }
-  int64_t work_threads = vec ? ceil_div64(n, kPx) : n;
-  int64_t blocks = ceil_div64(work_threads > 0 ? work_threads : 1, 256);
-  int64_t cap = (int64_t)sms * ctas_per_sm;
+  constexpr int kPxPerCtaIter = (kConfThreads / 32) * 32 * ChunkOf<L, P>::kPL * ChunkOf<L, P>::kUnroll;
+  int64_t blocks = ceil_div64(n, kPxPerCtaIter);
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
-  MDSEG_REQUIRE(ceil_div64(n, blocks) < (int64_t)0xffffffffLL, "mdseg_confusion: n too large for one launch");
-  // err_flag may be NULL: point at a scratch word inside hist? No — require it.
-  auto* h = reinterpret_cast<unsigned long long*>(hist);
-#define MDSEG_CONF_LAUNCH(SM, VE)                                                                             \
-  do {                                                                                                        \
-    auto k = confusion_kernel<L, P, SM, VE>;                                                                  \
-    if (smem > 48 * 1024) MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<(unsigned)blocks, 256, smem, st>>>((const L*)label, (const P*)pred, lut, h, Ca, Cb, ignore, n, err_flag, replicas); \
-  } while (0)
-  if (use_smem) { if (vec) MDSEG_CONF_LAUNCH(true, true); else MDSEG_CONF_LAUNCH(true, false); }
-  else          { if (vec) MDSEG_CONF_LAUNCH(false, true); else MDSEG_CONF_LAUNCH(false, false); }
-#undef MDSEG_CONF_LAUNCH
+  auto k = confusion_kernel<L, P>;
+  if (smem > 48 * 1024) MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)blocks, kConfThreads, smem, st>>>((const L*)label, (const P*)pred, lut,
+                                                  reinterpret_cast<unsigned long long*>(hist), Ca, Cb, ignore, n,
+                                                  err_flag, replicas, aligned ? 1 : 0);
   MDSEG_LAUNCH_OK();
   return 0;
 }

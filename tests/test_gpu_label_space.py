@@ -92,6 +92,32 @@ def test_confusion_piecewise_constant_and_lut(ops):
     assert np.array_equal(hist.cpu().numpy(), ls.confusion(ls.lut_gather(raw, lut), pred, 19))
 
 
+@pytest.mark.parametrize("lab_dt,pred_dt", [(torch.int64, torch.int64), (torch.uint8, torch.int64),
+                                            (torch.uint8, torch.uint8), (torch.int32, torch.int32),
+                                            (torch.int64, torch.uint8), (torch.uint8, torch.int32)])
+@pytest.mark.parametrize("mean_run", [1.5, 7, 40, 700])
+@pytest.mark.parametrize("offset", [0, 3])
+def test_confusion_runs_across_lanes(ops, lab_dt, pred_dt, mean_run, offset):
+    """Runs of random length (shorter than a lane's pixels up to several warp chunks) with ignored stretches:
+    the warp-level run merge must count every pixel exactly once for every element-width pairing; offset 3
+    takes the unaligned (scalar) route."""
+    rng = np.random.default_rng(int(mean_run * 10) + offset)
+    n = 200003
+    def runs(C, p_ignore):
+        lens = rng.geometric(1.0 / mean_run, size=int(1.3 * n / mean_run) + 64)
+        vals = rng.integers(0, C, lens.size)
+        vals[rng.random(lens.size) < p_ignore] = 255
+        return np.repeat(vals, lens)[:n + offset]
+    lab = runs(37, 0.1)
+    pred = np.minimum(runs(37, 0.0), 36)
+    assert lab.size == n + offset and pred.size == n + offset
+    l = torch.from_numpy(lab).to(lab_dt).to(DEV)[offset:]
+    p = torch.from_numpy(pred).to(pred_dt).to(DEV)[offset:]
+    hist = ops.confusion(l, p, 37)
+    assert np.array_equal(hist.cpu().numpy(), ls.confusion(lab[offset:], pred[offset:], 37))
+    ops.check_errors(DEV)
+
+
 def test_confusion_flags_bad_labels(ops):
     lab = torch.tensor([0, 1, 19, 255, 2], device=DEV)  # 19 is out of range for C=19
     pred = torch.tensor([0, 1, 1, 1, 2], device=DEV)
