@@ -251,6 +251,21 @@ int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table* graphs /*h
                    float* y, int y_cmax, float* cmax_out /* optional fp32 [n_images,h,w]: max_n y */,
                    int32_t* err_flag, void* stream);
 
+/* The same projection with the DENSE graphs (GNN stage: soft adjacency with grad,
+ * loss_cross_datasets.py:997-1006) on the tcgen05 tensor cores: a [128 px, C_uni] x
+ * [C_uni, C_ds] tile per CTA, fp32 accumulators in TMEM.  fp32 inputs are split into
+ * three bf16 terms per operand (six products, relative error ~2^-21); bf16 / fp16
+ * inputs take one product in their own type with G rounded to it (what autocast does
+ * to the reference einsum).  Datasets with a sparse graph, or a dense one outside the
+ * envelope (C_ds < 8, C_ds > 256, C_uni < 32), go through the kernels of
+ * mdseg_proj_fwd inside the same call.  `workspace` (caller-owned, device) receives the
+ * converted graphs; it is rewritten on every call, so graphs may change between calls. */
+size_t mdseg_proj_fwd_tc_workspace_bytes(const mdseg_graph_table* graphs /*host*/, int dtype);
+int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_table* graphs /*host*/,
+                      const int32_t* dataset_ids, int n_images, int h, int w,
+                      float* y, int y_cmax, float* cmax_out, void* workspace,
+                      size_t workspace_bytes, int32_t* err_flag, void* stream);
+
 /* dx[b, c, :, :] = Σ_n G_d[n, c] * (dyA[b, n] + dyB[b, n]); dyB may be NULL.
  * dx has dtype of x and is fully overwritten (zeros for images whose dataset
  * id is out of range). */

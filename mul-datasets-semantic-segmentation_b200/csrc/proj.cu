@@ -183,10 +183,10 @@ template <typename TIn, typename TOut, bool kFwd>
 __global__ void __launch_bounds__(256)
 proj_dense_kernel(const TIn* __restrict__ in, const float* __restrict__ in2, const mdseg_graph_table tab,
                   const int32_t* __restrict__ dataset_ids, int64_t hw, int in_cstride, int out_cstride,
-                  TOut* __restrict__ out) {
+                  TOut* __restrict__ out, unsigned skip_mask) {
   const int b = blockIdx.z;
   const int d = dataset_ids ? dataset_ids[b] : 0;
-  if (d < 0 || d >= tab.n_datasets) return;
+  if (d < 0 || d >= tab.n_datasets || ((skip_mask >> d) & 1u)) return;
   const mdseg_sparse_graph g = tab.g[d];
   if (!g.dense) return;
   const int K = kFwd ? tab.C_uni : g.C_ds;
@@ -315,9 +315,9 @@ proj_dgraph_kernel(const T* __restrict__ x, const float* __restrict__ dyA, const
     }
 }
 
-bool any_dense(const mdseg_graph_table* t) {
+bool any_dense(const mdseg_graph_table* t, unsigned skip_mask = 0) {
   for (int i = 0; i < t->n_datasets; ++i)
-    if (t->g[i].dense) return true;
+    if (t->g[i].dense && !((skip_mask >> i) & 1u)) return true;
   return false;
 }
 bool any_sparse(const mdseg_graph_table* t) {
@@ -345,7 +345,7 @@ int check_table(const mdseg_graph_table* t, const char* who) {
 
 template <typename T>
 int launch_fwd(const void* x, const mdseg_graph_table* t, const int32_t* ids, int n_images, int64_t hw, float* y,
-               int y_cmax, float* cmax, int32_t* ef, cudaStream_t s) {
+               int y_cmax, float* cmax, int32_t* ef, unsigned skip_mask, cudaStream_t s) {
   constexpr int PXV = 16 / sizeof(T);
   if (any_sparse(t)) {
     const bool vec = (hw % PXV == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
@@ -358,9 +358,10 @@ int launch_fwd(const void* x, const mdseg_graph_table* t, const int32_t* ids, in
     else proj_fwd_sparse_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, *t, ids, hw, y, y_cmax, cmax, ef);
     MDSEG_LAUNCH_OK();
   }
-  if (any_dense(t)) {
+  if (any_dense(t, skip_mask)) {
     dim3 grid((unsigned)ceil_div64(hw, kTP), (unsigned)((max_cds(t) + kTO - 1) / kTO), (unsigned)n_images);
-    proj_dense_kernel<T, float, true><<<grid, 256, 0, s>>>((const T*)x, nullptr, *t, ids, hw, t->C_uni, y_cmax, y);
+    proj_dense_kernel<T, float, true><<<grid, 256, 0, s>>>((const T*)x, nullptr, *t, ids, hw, t->C_uni, y_cmax, y,
+                                                           skip_mask);
     MDSEG_LAUNCH_OK();
   }
   return 0;
@@ -383,7 +384,7 @@ int launch_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph
   }
   if (any_dense(t)) {
     dim3 grid((unsigned)ceil_div64(hw, kTP), (unsigned)((t->C_uni + kTO - 1) / kTO), (unsigned)n_images);
-    proj_dense_kernel<float, T, false><<<grid, 256, 0, s>>>(dyA, dyB, *t, ids, hw, y_cmax, t->C_uni, (T*)dx);
+    proj_dense_kernel<float, T, false><<<grid, 256, 0, s>>>(dyA, dyB, *t, ids, hw, y_cmax, t->C_uni, (T*)dx, 0u);
     MDSEG_LAUNCH_OK();
   }
   return 0;
@@ -404,24 +405,32 @@ int launch_dgraph(const void* x, const float* dyA, const float* dyB, int y_cmax,
 }  // namespace
 }  // namespace mdseg
 
-extern "C" int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table* graphs, const int32_t* dataset_ids,
-                              int n_images, int h, int w, float* y, int y_cmax, float* cmax_out, int32_t* err_flag,
-                              void* stream) {
-  using namespace mdseg;
+namespace mdseg {
+// Projection of every dataset whose bit is clear in skip_mask (the tensor-core kernel of proj_tc.cu takes the rest).
+int proj_fwd_rest(const void* x, int dtype, const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images,
+                  int h, int w, float* y, int y_cmax, float* cmax_out, int32_t* err_flag, unsigned skip_mask,
+                  cudaStream_t s) {
   if (int rc = check_table(graphs, "mdseg_proj_fwd")) return rc;
   MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0, "mdseg_proj_fwd: bad shape");
   MDSEG_REQUIRE(y_cmax >= max_cds(graphs), "mdseg_proj_fwd: y_cmax %d < max C_ds %d", y_cmax, max_cds(graphs));
   if (n_images == 0) return 0;
   MDSEG_REQUIRE(x && y, "mdseg_proj_fwd: null pointer");
   const int64_t hw = (int64_t)h * w;
-  cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case MDSEG_F32: return launch_fwd<float>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, s);
-    case MDSEG_BF16: return launch_fwd<__nv_bfloat16>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, s);
-    case MDSEG_F16: return launch_fwd<__half>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, s);
+    case MDSEG_F32: return launch_fwd<float>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, skip_mask, s);
+    case MDSEG_BF16: return launch_fwd<__nv_bfloat16>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, skip_mask, s);
+    case MDSEG_F16: return launch_fwd<__half>(x, graphs, dataset_ids, n_images, hw, y, y_cmax, cmax_out, err_flag, skip_mask, s);
   }
   set_error("mdseg_proj_fwd: unsupported dtype %d", dtype);
   return 2;
+}
+}  // namespace mdseg
+
+extern "C" int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table* graphs, const int32_t* dataset_ids,
+                              int n_images, int h, int w, float* y, int y_cmax, float* cmax_out, int32_t* err_flag,
+                              void* stream) {
+  return mdseg::proj_fwd_rest(x, dtype, graphs, dataset_ids, n_images, h, w, y, y_cmax, cmax_out, err_flag, 0u,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int mdseg_proj_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* graphs,

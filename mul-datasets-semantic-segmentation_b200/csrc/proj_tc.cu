@@ -1,0 +1,409 @@
+// proj_tc.cu — dense bipartite projection on the 5th-generation tensor cores (GNN stage).
+//
+// Reference work replaced (lib/loss/loss_cross_datasets.py:1006, :997/:1000; lib/models/semseg.py:344):
+//   remap_logit = torch.einsum('bchw, nc -> bnhw', logits[dataset_ids==i], bi_graphs[i])
+// with a DENSE fp32 bi_graph (soft adjacency of the GNN stage, requires_grad): a real
+// [B_i*h*w, C_uni] x [C_uni, C_ds] contraction (cfg3 / ADE: 2*358*150 FLOP per low-res pixel).
+//
+// GEMM shape per CTA tile:  D[M = 128 pixels, N = C_ds padded to 16] += A[M, K] * B[N, K]^T,  K = C_uni.
+//   * A = x^T: pixels are contiguous in HBM (NCHW), so a thread owns one pixel and half of a 32-channel
+//     K-chunk (256 threads per 128-pixel tile), reads its 16 channels with warp-coalesced loads, converts
+//     to 16-bit terms and writes them K-major into the canonical no-swizzle core-matrix layout (8 rows x
+//     16 bytes per core matrix) in shared memory.
+//   * B = G_d: split / converted ONCE by a prep kernel into the same layout in a caller-owned workspace;
+//     each K-chunk arrives with one cp.async.bulk (mbarrier complete_tx).
+//   * one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM); tcgen05.commit frees a
+//     shared-memory stage and, after the last chunk, hands the accumulator to the epilogue;
+//   * epilogue: tcgen05.ld (32 lanes x 32 bit, 16 columns at a time) -> coalesced fp32 stores of y[n][p].
+// Precision: fp32 inputs are split into three bf16 terms each (x = xh + xm + xl, G likewise) and the six
+// products of weight >= 2^-16 are accumulated (relative error ~2^-21, inside the 1e-5 parity bar without
+// giving up fp32's range); bf16 / fp16 inputs take ONE product in their own type, G rounded to it — what
+// autocast does to the reference einsum.
+#include "common.cuh"
+
+namespace mdseg {
+// proj.cu: the same projection without the tensor-core datasets (bit d of skip_mask = dataset d is handled here)
+int proj_fwd_rest(const void* x, int dtype, const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images,
+                  int h, int w, float* y, int y_cmax, float* cmax_out, int32_t* err_flag, unsigned skip_mask,
+                  cudaStream_t s);
+
+namespace {
+
+constexpr int kTM = 128;      // pixels per tile = UMMA M
+constexpr int kKB = 32;       // channels per shared-memory stage (two K = 16 MMA steps)
+constexpr int kStagesTc = 2;
+constexpr int kTcThreads = 2 * kTM;  // two threads per pixel: 16 channels of a chunk each
+constexpr int kMaxN = 256;    // UMMA N limit
+
+__host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
+
+struct TcArgs {
+  const void* x;
+  float* y;
+  const int32_t* dataset_ids;
+  const unsigned char* gw;               // prepared graphs (workspace)
+  long long g_off[MDSEG_MAX_DATASETS];   // byte offset of dataset d's chunks
+  int C_ds[MDSEG_MAX_DATASETS];
+  unsigned tc_mask;                      // datasets handled by this kernel
+  int n_datasets, C_uni, y_cmax;
+  long long hw;
+  int n_chunks;
+  int a_stage_bytes, b_stage_bytes;      // per stage, all terms
+  int fmt;                               // UMMA 16-bit format: 0 = F16, 1 = BF16
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier / bulk copy -----------------------------------------------------------------------------
+__device__ __forceinline__ void bar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MDSEG_TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MDSEG_TC_DONE;\n"
+      "bra MDSEG_TC_WAIT;\n"
+      "MDSEG_TC_DONE:\n"
+      "}\n" ::"r"(smem_addr(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// ---- tcgen05 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, 16-bit inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1):
+// core matrix = 8 rows x 16 bytes stored contiguously; `sbo` = bytes between 8-row groups (M / N direction),
+// `lbo` = bytes between the core matrices adjacent in K.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A and B K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(int fmt, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+}
+
+// ---- 16-bit terms of fp32 values ------------------------------------------------------------------------
+template <int TERMS> struct Split;  // pack two consecutive-K values into one 32-bit word per term
+template <> struct Split<3> {
+  static __device__ __forceinline__ void pair(float a, float b, int /*fmt*/, uint32_t (&o)[3]) {
+    float ra = a, rb = b;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(ra, rb);
+      o[t] = *reinterpret_cast<const uint32_t*>(&h);
+      ra -= __low2float(h);
+      rb -= __high2float(h);
+    }
+  }
+};
+template <> struct Split<1> {
+  static __device__ __forceinline__ void pair(float a, float b, int fmt, uint32_t (&o)[1]) {
+    if (fmt == 1) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      o[0] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __half2 h = __floats2half2_rn(a, b);
+      o[0] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+};
+
+// ---- prep: G_d [C_ds, C_uni] fp32 -> per K-chunk, per term, canonical K-major core-matrix layout ---------
+// chunk (d, kc) holds TERMS blocks of [Npad rows][32 k]: byte offset of (term t, row n, k) inside the chunk =
+// t * Npad * 64 + (k / 8) * (Npad * 16) + n * 16 + (k % 8) * 2.
+template <int TERMS>
+__global__ void __launch_bounds__(256) proj_tc_prep_kernel(const mdseg_graph_table tab, unsigned tc_mask, int n_chunks,
+                                                           int fmt, unsigned char* gw, const TcArgs a) {
+  const int d = blockIdx.y;
+  if (!((tc_mask >> d) & 1u)) return;
+  const mdseg_sparse_graph g = tab.g[d];
+  const int npad = pad16(g.C_ds);
+  const int groups = n_chunks * 4 * npad;  // (chunk, k-group of 8, row)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += gridDim.x * blockDim.x) {
+    const int n = i % npad, kg = (i / npad) % 4, kc = i / (4 * npad);
+    uint32_t w[TERMS][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = kc * kKB + kg * 8 + 2 * j;
+      float v0 = 0.f, v1 = 0.f;
+      if (n < g.C_ds) {
+        if (c < tab.C_uni) v0 = g.dense[(int64_t)n * tab.C_uni + c];
+        if (c + 1 < tab.C_uni) v1 = g.dense[(int64_t)n * tab.C_uni + c + 1];
+      }
+      uint32_t o[TERMS];
+      Split<TERMS>::pair(v0, v1, fmt, o);
+#pragma unroll
+      for (int t = 0; t < TERMS; ++t) w[t][j] = o[t];
+    }
+    unsigned char* chunk = gw + a.g_off[d] + (int64_t)kc * TERMS * npad * 64;
+#pragma unroll
+    for (int t = 0; t < TERMS; ++t)
+      *reinterpret_cast<uint4*>(chunk + (int64_t)t * npad * 64 + kg * (npad * 16) + n * 16) =
+          make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+  }
+}
+
+// ---- main kernel -------------------------------------------------------------------------------------------
+template <typename T, int TERMS>
+__global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_b[kStagesTc];    // B chunk landed (bulk copy complete_tx)
+  __shared__ __align__(8) uint64_t bar_mma[kStagesTc];  // the MMAs that read the stage have retired
+  __shared__ __align__(8) uint64_t bar_acc;             // accumulator complete
+  __shared__ uint32_t tmem_base_s;
+
+  const int b = blockIdx.y;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  if (d < 0 || d >= a.n_datasets || !((a.tc_mask >> d) & 1u)) return;  // uniform per CTA
+  const int C_ds = a.C_ds[d];
+  const int npad = pad16(C_ds);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (kTM - 1), khalf = tid >> 7;  // pixel of the tile, half of the K-chunk
+  const long long p = (long long)blockIdx.x * kTM + row;
+  const bool p_ok = p < a.hw;
+
+  unsigned char* sA = smem;                                        // [stage][term][4 k-groups][128 rows][16 B]
+  unsigned char* sB = smem + (size_t)kStagesTc * a.a_stage_bytes;   // [stage][term][4 k-groups][npad rows][16 B]
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < npad) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesTc; ++s) { bar_init(&bar_b[s], 1); bar_init(&bar_mma[s], 1); }
+    bar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  const T* xb = (const T*)a.x + (long long)b * a.C_uni * a.hw;
+  const unsigned char* gchunks = a.gw + a.g_off[d];
+  const uint32_t b_chunk_bytes = (uint32_t)(TERMS * npad * 64);
+  const uint32_t idesc = umma_idesc(a.fmt, npad);
+
+  // this thread's 16 channels of a chunk, one chunk ahead in registers so that the HBM latency of chunk kc + 1
+  // hides behind the conversion, the hand-over and the stage wait of chunk kc
+  float vn[kKB / 2];
+  auto load_chunk = [&](int kc) {
+#pragma unroll
+    for (int j = 0; j < kKB / 2; ++j) {
+      const int c = kc * kKB + khalf * (kKB / 2) + j;
+      vn[j] = (p_ok && c < a.C_uni) ? to_f32<T>(xb[(long long)c * a.hw + p]) : 0.f;
+    }
+  };
+  load_chunk(0);
+
+  for (int kc = 0; kc < a.n_chunks; ++kc) {
+    const int s = kc % kStagesTc;
+    const uint32_t use = (uint32_t)(kc / kStagesTc);
+    float v[kKB / 2];
+#pragma unroll
+    for (int j = 0; j < kKB / 2; ++j) v[j] = vn[j];
+    if (kc + 1 < a.n_chunks) load_chunk(kc + 1);
+    // the MMAs of chunk kc - kStages have finished reading stage s
+    if (kc >= kStagesTc) bar_wait(&bar_mma[s], (use - 1) & 1u);
+    unsigned char* stA = sA + (size_t)s * a.a_stage_bytes;
+    unsigned char* stB = sB + (size_t)s * a.b_stage_bytes;
+    if (tid == 0) {
+      bar_expect_tx(&bar_b[s], b_chunk_bytes);
+      bulk_load(stB, gchunks + (size_t)kc * b_chunk_bytes, b_chunk_bytes, &bar_b[s]);
+    }
+    // A: this thread's pixel, 16 channels -> TERMS x 2 k-groups x 16 bytes
+#pragma unroll
+    for (int kq = 0; kq < 2; ++kq) {
+      const int kg = 2 * khalf + kq;
+      uint32_t w[TERMS][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t o[TERMS];
+        Split<TERMS>::pair(v[kq * 8 + 2 * j], v[kq * 8 + 2 * j + 1], a.fmt, o);
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t) w[t][j] = o[t];
+      }
+#pragma unroll
+      for (int t = 0; t < TERMS; ++t)
+        *reinterpret_cast<uint4*>(stA + t * (4 * kTM * 16) + kg * (kTM * 16) + row * 16) =
+            make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+    }
+    // generic-proxy writes -> visible to the tensor core's async proxy, then hand over to the issuing thread
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      bar_wait(&bar_b[s], use & 1u);
+      tc_fence_after();
+      const uint32_t aA = smem_addr(stA), aB = smem_addr(stB);
+#pragma unroll
+      for (int ks = 0; ks < kKB / 16; ++ks) {
+        // products in order of decreasing weight; TERMS == 1: just (0, 0)
+        constexpr int kPairs = TERMS == 3 ? 6 : 1;
+        const int ta[6] = {0, 0, 1, 1, 0, 2};
+        const int tb[6] = {0, 1, 0, 1, 2, 0};
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+          const uint64_t ad = umma_desc(aA + ta[q] * (4 * kTM * 16) + ks * 2 * (kTM * 16), kTM * 16, 128);
+          const uint64_t bd = umma_desc(aB + tb[q] * (npad * 64) + ks * 2 * (npad * 16), npad * 16, 128);
+          umma_f16(tmem_d, ad, bd, idesc, (kc > 0 || ks > 0 || q > 0) ? 1u : 0u);
+        }
+      }
+      tc_commit(&bar_mma[s]);                       // frees the stage when these MMAs retire
+      if (kc == a.n_chunks - 1) tc_commit(&bar_acc);  // ... and the accumulator is complete
+    }
+  }
+
+  // epilogue: warp w reads TMEM lanes 32(w % 4) .. +31 (= pixels of this tile); the two warps that share a lane
+  // quarter take alternate groups of 16 columns
+  bar_wait(&bar_acc, 0);
+  tc_fence_after();
+  float* yb = a.y + (long long)b * a.y_cmax * a.hw;
+  for (int n0 = (warp >> 2) * 16; n0 < npad; n0 += 32) {
+    float acc[16];
+    tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)n0, acc);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (p_ok && n0 + i < C_ds) yb[(long long)(n0 + i) * a.hw + p] = acc[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+bool tc_dataset(const mdseg_sparse_graph& g, int C_uni) {
+  return g.dense != nullptr && g.C_ds >= 8 && g.C_ds <= kMaxN && C_uni >= 32;
+}
+int terms_of(int dtype) { return dtype == MDSEG_F32 ? 3 : 1; }
+
+}  // namespace
+}  // namespace mdseg
+
+extern "C" size_t mdseg_proj_fwd_tc_workspace_bytes(const mdseg_graph_table* graphs, int dtype) {
+  using namespace mdseg;
+  if (!graphs || graphs->n_datasets <= 0 || graphs->n_datasets > MDSEG_MAX_DATASETS || graphs->C_uni <= 0) return 256;
+  const int n_chunks = (graphs->C_uni + kKB - 1) / kKB;
+  size_t total = 256;
+  for (int i = 0; i < graphs->n_datasets; ++i)
+    if (tc_dataset(graphs->g[i], graphs->C_uni))
+      total += (size_t)n_chunks * terms_of(dtype) * pad16(graphs->g[i].C_ds) * 64;
+  return total;
+}
+
+extern "C" int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_table* graphs, const int32_t* dataset_ids,
+                                 int n_images, int h, int w, float* y, int y_cmax, float* cmax_out, void* workspace,
+                                 size_t workspace_bytes, int32_t* err_flag, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(graphs && graphs->n_datasets > 0 && graphs->n_datasets <= MDSEG_MAX_DATASETS && graphs->C_uni > 0,
+                "mdseg_proj_fwd_tc: bad graph table");
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0, "mdseg_proj_fwd_tc: bad shape");
+  MDSEG_REQUIRE(is_float_dtype(dtype), "mdseg_proj_fwd_tc: unsupported dtype %d", dtype);
+  if (n_images == 0) return 0;
+  MDSEG_REQUIRE(x && y && workspace, "mdseg_proj_fwd_tc: null pointer");
+  MDSEG_REQUIRE(workspace_bytes >= mdseg_proj_fwd_tc_workspace_bytes(graphs, dtype),
+                "mdseg_proj_fwd_tc: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+
+  TcArgs a;
+  a.x = x; a.y = y; a.dataset_ids = dataset_ids;
+  a.gw = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  a.n_datasets = graphs->n_datasets; a.C_uni = graphs->C_uni; a.y_cmax = y_cmax;
+  a.hw = (long long)h * w;
+  a.n_chunks = (graphs->C_uni + kKB - 1) / kKB;
+  a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  const int terms = terms_of(dtype);
+  a.tc_mask = 0;
+  int npad_max = 0;
+  long long off = 0;
+  for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
+    a.g_off[i] = 0; a.C_ds[i] = 0;
+    if (i >= graphs->n_datasets) continue;
+    a.C_ds[i] = graphs->g[i].C_ds;
+    if (!tc_dataset(graphs->g[i], graphs->C_uni)) continue;
+    MDSEG_REQUIRE(y_cmax >= graphs->g[i].C_ds, "mdseg_proj_fwd_tc: y_cmax %d < C_ds %d", y_cmax, graphs->g[i].C_ds);
+    a.tc_mask |= 1u << i;
+    a.g_off[i] = off;
+    off += (long long)a.n_chunks * terms * pad16(graphs->g[i].C_ds) * 64;
+    npad_max = pad16(graphs->g[i].C_ds) > npad_max ? pad16(graphs->g[i].C_ds) : npad_max;
+  }
+  // sparse graphs and dense ones outside the tensor-core envelope: the CSR / FFMA kernels of proj.cu
+  if (int rc = proj_fwd_rest(x, dtype, graphs, dataset_ids, n_images, h, w, y, y_cmax, cmax_out, err_flag, a.tc_mask, s))
+    return rc;
+  if (!a.tc_mask) return 0;
+
+  a.a_stage_bytes = terms * 4 * kTM * 16;
+  a.b_stage_bytes = terms * npad_max * 64;
+  const size_t smem = (size_t)kStagesTc * (a.a_stage_bytes + a.b_stage_bytes);
+  const dim3 pgrid((unsigned)((a.n_chunks * 4 * npad_max + 255) / 256), (unsigned)graphs->n_datasets);
+  const dim3 grid((unsigned)((a.hw + kTM - 1) / kTM), (unsigned)n_images);
+#define MDSEG_TC_LAUNCH(T, TERMS)                                                                                  \
+  do {                                                                                                             \
+    proj_tc_prep_kernel<TERMS><<<pgrid, 256, 0, s>>>(*graphs, a.tc_mask, a.n_chunks, a.fmt,                        \
+                                                     const_cast<unsigned char*>(a.gw), a);                         \
+    MDSEG_LAUNCH_OK();                                                                                             \
+    auto k = proj_tc_kernel<T, TERMS>;                                                                             \
+    MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    k<<<grid, kTcThreads, smem, s>>>(a);                                                                                  \
+    MDSEG_LAUNCH_OK();                                                                                             \
+  } while (0)
+  switch (dtype) {
+    case MDSEG_F32: MDSEG_TC_LAUNCH(float, 3); break;
+    case MDSEG_BF16: MDSEG_TC_LAUNCH(__nv_bfloat16, 1); break;
+    case MDSEG_F16: MDSEG_TC_LAUNCH(__half, 1); break;
+  }
+#undef MDSEG_TC_LAUNCH
+  return 0;
+}

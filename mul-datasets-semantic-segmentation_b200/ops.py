@@ -495,9 +495,20 @@ def project(logits_uni, graphs, dataset_ids=None, cache=None):
     cmax = max(g.shape[0] for g in graphs)
     ids = _ids32(dataset_ids, B, x.device)
     y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=x.device)
-    N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, None,
-           _ptr(err_flag(x.device)), _stream())
+    _proj_fwd(x, tab, ids, B, h, w, y, cmax, None, err_flag(x.device))
     return y
+
+
+def _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef):
+    """mdseg_proj_fwd, or mdseg_proj_fwd_tc (dense graphs on the tensor cores) when a graph is dense."""
+    if any(tab.g[i].dense for i in range(tab.n_datasets)):
+        nbytes = N.lib.mdseg_proj_fwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        N.call("mdseg_proj_fwd_tc", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, _ptr(ymax),
+               _ptr(ws), nbytes, _ptr(ef), _stream())
+    else:
+        N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, _ptr(ymax),
+               _ptr(ef), _stream())
 
 
 # ---- a5+a6+a7+a8+a9: the fused multi-dataset loss ------------------------------------------------------
@@ -528,8 +539,7 @@ class _MdsProjOhemCE(torch.autograd.Function):
         y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=dev)
         ymax = torch.empty(B, h, w, dtype=torch.float32, device=dev)  # channel maximum of y: the softmax shift
         all_sparse = all(not tab.g[i].dense for i in range(len(Cs)))
-        N.call("mdseg_proj_fwd", _ptr(x), _DT[x.dtype], C.byref(tab), _ptr(ids), B, h, w, _ptr(y), cmax, _ptr(ymax),
-               _ptr(ef), _stream())
+        _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef)
         src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, False, c_alloc=cmax,
                          cmax=ymax, cmax_ready=all_sparse)
         P = B * H * W
