@@ -171,7 +171,7 @@ __device__ __forceinline__ void broadcast_chunk(const Unit& un, TO* orow, const 
   const bool col_ok = 4 * t < un.ncols;
   TO* base = orow + 4 * t;
   asm volatile("" : "+l"(base));
-#pragma unroll 2
+#pragma unroll 4
   for (int q = q0; q < q1; ++q) {
     const uint32_t e = ents[4 * q + o];
     if (col_ok && e != kNoEnt) {
@@ -267,10 +267,13 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
 
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
+    // corners of the next class are fetched while the current one is being computed (the loop stays rolled)
+    float n00 = Sp[0], n01 = Sp[1], n10 = Sp[kBoxW], n11 = Sp[kBoxW + 1];
 #pragma unroll 1
     for (int c = 0; c < cc; ++c) {
-      float v00 = Sp[0], v01 = Sp[1], v10 = Sp[kBoxW], v11 = Sp[kBoxW + 1];
+      float v00 = n00, v01 = n01, v10 = n10, v11 = n11;
       Sp += 2 * kBoxW;
+      if (c + 1 < cc) { n00 = Sp[0]; n01 = Sp[1]; n10 = Sp[kBoxW]; n11 = Sp[kBoxW + 1]; }
       if (!a.src_scaled) { v00 *= kLog2e; v01 *= kLog2e; v10 *= kLog2e; v11 *= kLog2e; }
       const float dv0 = v01 - v00, dv1 = v11 - v10;
       const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
