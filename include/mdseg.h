@@ -355,6 +355,33 @@ int mdseg_eval_accum(const void* logits, int dtype, int C, int h, int w,
                      float* probs, int H, int W, int flip, int first,
                      void* stream);
 
+/* ---- a11 + a12 fused over all passes of one image ------------------
+ * pred[p] = argmax_c Σ_s softmax_c(upsample(logits_s (mirrored along W if flip_s))[., p]),
+ * hist[label[p] * C + pred[p]] += 1 for label != ignore — evaluate.py:136-181 for one
+ * image with every (scale, flip) pass at hand, without the [C, H, W] probability tensor:
+ * the per-pass soft-max statistics (8 bytes per pixel and pass) go to `workspace`, the
+ * class accumulators live in registers.  The sums are bit-identical to mdseg_eval_accum
+ * pass by pass followed by mdseg_argmax_hist.  pred (int64 [H*W]) and hist (int64 [C*C],
+ * accumulated into) are each optional. */
+#define MDSEG_MAX_EVAL_PASSES 16
+typedef struct mdseg_eval_pass {
+  const void* logits; /* device, [C, h, w] */
+  int h, w;
+  int flip;
+  int reserved;
+} mdseg_eval_pass;
+typedef struct mdseg_eval_passes {
+  mdseg_eval_pass p[MDSEG_MAX_EVAL_PASSES];
+  int n_passes;
+  int dtype; /* MDSEG_F32 / BF16 / F16, common to all passes */
+} mdseg_eval_passes;
+size_t mdseg_eval_fused_workspace_bytes(int n_passes, int H, int W);
+int mdseg_eval_fused(const mdseg_eval_passes* passes /*host*/, int C, int H, int W,
+                     int64_t* pred, const void* label, int label_dtype,
+                     const uint8_t* lut256, int64_t* hist, int ignore,
+                     void* workspace, size_t workspace_bytes,
+                     int32_t* err_flag, void* stream);
+
 /* pred[p] = argmax_c probs[c, p] (first maximal index, like torch.argmax on
  * distinct values); optionally fused with the confusion matrix update
  * (label/hist may be NULL).  evaluate.py:172-181. */

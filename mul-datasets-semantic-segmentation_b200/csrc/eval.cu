@@ -17,6 +17,48 @@
 namespace mdseg {
 namespace {
 
+// One label pixel of one pass: its four low-resolution corners (class 0) and interpolation weights.
+template <typename T> struct EvalPixel {
+  const T *q00, *q01, *q10, *q11;
+  float l0h, l1h, l0w, l1w;
+  __device__ __forceinline__ float at(int64_t o) const {
+    return l0h * (l0w * to_f32<T>(q00[o]) + l1w * to_f32<T>(q01[o])) +
+           l1h * (l0w * to_f32<T>(q10[o]) + l1w * to_f32<T>(q11[o]));
+  }
+};
+constexpr int kEvBlk = 8;  // classes per block: 32 independent loads in flight per thread
+
+// Soft-max statistics of the pixel over C classes (class stride hw): the running maximum is updated once per
+// block of eight classes, so a block costs nine exponentials and its 32 loads are independent.  Both evaluator
+// kernels use this function and the same block order, which is what makes their sums bit-identical.
+template <typename T>
+__device__ __forceinline__ void eval_softmax_stats(const EvalPixel<T>& px, int C, int64_t hw, float& m, float& inv) {
+  m = -FLT_MAX;
+  float sum = 0.f;
+  int c = 0;
+  for (; c + kEvBlk <= C; c += kEvBlk) {
+    float z[kEvBlk];
+#pragma unroll
+    for (int i = 0; i < kEvBlk; ++i) z[i] = px.at((int64_t)(c + i) * hw);
+    float mb = z[0];
+#pragma unroll
+    for (int i = 1; i < kEvBlk; ++i) mb = fmaxf(mb, z[i]);
+    const float mn = fmaxf(m, mb);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < kEvBlk; ++i) part += ex2_approx((z[i] - mn) * kLog2e);
+    sum = sum * ex2_approx((m - mn) * kLog2e) + part;
+    m = mn;
+  }
+  for (; c < C; ++c) {
+    const float z = px.at((int64_t)c * hw);
+    const float mn = fmaxf(m, z);
+    sum = sum * ex2_approx((m - mn) * kLog2e) + ex2_approx((z - mn) * kLog2e);
+    m = mn;
+  }
+  inv = 1.0f / sum;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 eval_accum_kernel(const T* __restrict__ logits, int C, int h, int w, float* __restrict__ probs, int H, int W,
@@ -29,23 +71,26 @@ eval_accum_kernel(const T* __restrict__ logits, int C, int h, int w, float* __re
     ym.at(Y, y0, y1, l0h, l1h);
     xm.at(X, x0, x1, l0w, l1w);
     if (flip) { x0 = w - 1 - x0; x1 = w - 1 - x1; }  // torch.flip(logits, dims=(3,)) before interpolate
-    const int64_t o00 = (int64_t)y0 * w + x0, o01 = (int64_t)y0 * w + x1;
-    const int64_t o10 = (int64_t)y1 * w + x0, o11 = (int64_t)y1 * w + x1;
-    float m = -FLT_MAX, s = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const T* q = logits + (int64_t)c * hw;
-      const float z = l0h * (l0w * to_f32<T>(q[o00]) + l1w * to_f32<T>(q[o01])) +
-                      l1h * (l0w * to_f32<T>(q[o10]) + l1w * to_f32<T>(q[o11]));
-      const float mn = fmaxf(m, z);
-      s = s * ex2_approx((m - mn) * kLog2e) + ex2_approx((z - mn) * kLog2e);
-      m = mn;
+    EvalPixel<T> px;
+    px.q00 = logits + (int64_t)y0 * w + x0; px.q01 = logits + (int64_t)y0 * w + x1;
+    px.q10 = logits + (int64_t)y1 * w + x0; px.q11 = logits + (int64_t)y1 * w + x1;
+    px.l0h = l0h; px.l1h = l1h; px.l0w = l0w; px.l1w = l1w;
+    float m, inv;
+    eval_softmax_stats<T>(px, C, hw, m, inv);
+    int c = 0;
+    for (; c + kEvBlk <= C; c += kEvBlk) {
+      float z[kEvBlk];
+#pragma unroll
+      for (int i = 0; i < kEvBlk; ++i) z[i] = px.at((int64_t)(c + i) * hw);
+#pragma unroll
+      for (int i = 0; i < kEvBlk; ++i) {
+        const float pr = ex2_approx((z[i] - m) * kLog2e) * inv;
+        float* dst = probs + (int64_t)(c + i) * HW + p;
+        *dst = first ? pr : (*dst + pr);
+      }
     }
-    const float inv = 1.0f / s;
-    for (int c = 0; c < C; ++c) {
-      const T* q = logits + (int64_t)c * hw;
-      const float z = l0h * (l0w * to_f32<T>(q[o00]) + l1w * to_f32<T>(q[o01])) +
-                      l1h * (l0w * to_f32<T>(q[o10]) + l1w * to_f32<T>(q[o11]));
-      const float pr = ex2_approx((z - m) * kLog2e) * inv;
+    for (; c < C; ++c) {
+      const float pr = ex2_approx((px.at((int64_t)c * hw) - m) * kLog2e) * inv;
       float* dst = probs + (int64_t)c * HW + p;
       *dst = first ? pr : (*dst + pr);
     }
@@ -88,6 +133,103 @@ argmax_hist_kernel(const float* __restrict__ probs, int C, int64_t n_px, long lo
     __syncthreads();
     for (int i = threadIdx.x; i < bins; i += blockDim.x)
       if (sh_hist[i]) atomicAdd(&hist[i], (unsigned long long)sh_hist[i]);
+  }
+}
+
+// ---- all (scale, flip) passes of one image without a probability tensor ------------------------
+// The reference (and mdseg_eval_accum) read-modify-write a [C, H, W] fp32 probability tensor once per pass
+// (1.26 GB for ADE at 1024 x 2048, 12 passes, 30 GB of traffic per image).  Here:
+//   1. eval_stats_kernel: per pass and label pixel the soft-max statistics (max, 1 / sum) — 8 bytes;
+//   2. eval_fused_kernel: a thread owns a label pixel and walks the classes in blocks of 16 whose accumulators
+//      P[16] live in REGISTERS: for every pass it interpolates the block's logits on the fly and adds
+//      ex2(z - max) / sum in pass order, then folds the block into the running arg-max; finally the confusion
+//      matrix is updated.  The arithmetic and its order are those of eval_accum_kernel + argmax_hist_kernel, so
+//      both routes give bit-identical predictions.
+// Threads are tiled 16 x 16 over the label image so that a CTA's corner loads of one class cover a compact
+// low-resolution patch (the re-reads stay in L1 / L2).  HBM sees the logits, the statistics, label and prediction.
+constexpr int kEvTile = 16, kEvThreads = kEvTile * kEvTile;
+constexpr int kEvCB = 16;  // classes per register block
+
+struct EvalPassDev {
+  const void* logits;
+  AxisMap ym, xm;
+  int h, w, flip;
+};
+struct EvalPassesDev {
+  EvalPassDev p[MDSEG_MAX_EVAL_PASSES];
+  int n;
+};
+
+template <typename T>
+__device__ __forceinline__ EvalPixel<T> eval_pixel(const EvalPassDev& ep, int Y, int X) {
+  int y0, y1, x0, x1;
+  EvalPixel<T> px;
+  ep.ym.at(Y, y0, y1, px.l0h, px.l1h);
+  ep.xm.at(X, x0, x1, px.l0w, px.l1w);
+  if (ep.flip) { x0 = ep.w - 1 - x0; x1 = ep.w - 1 - x1; }  // torch.flip(logits, dims=(3,)) before interpolate
+  const T* base = (const T*)ep.logits;
+  px.q00 = base + (int64_t)y0 * ep.w + x0; px.q01 = base + (int64_t)y0 * ep.w + x1;
+  px.q10 = base + (int64_t)y1 * ep.w + x0; px.q11 = base + (int64_t)y1 * ep.w + x1;
+  return px;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEvThreads)
+eval_stats_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H, int W, float2* __restrict__ stats) {
+  const int Y = blockIdx.y * kEvTile + (threadIdx.x >> 4), X = blockIdx.x * kEvTile + (threadIdx.x & 15);
+  if (Y >= H || X >= W) return;
+  const int s = blockIdx.z;
+  const EvalPassDev& ep = ps.p[s];
+  const EvalPixel<T> px = eval_pixel<T>(ep, Y, X);
+  float m, inv;
+  eval_softmax_stats<T>(px, C, (int64_t)ep.h * ep.w, m, inv);
+  stats[((int64_t)s * H + Y) * W + X] = make_float2(m, inv);
+}
+
+template <typename T, typename L>
+__global__ void __launch_bounds__(kEvThreads)
+eval_fused_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H, int W, const float2* __restrict__ stats,
+                  long long* __restrict__ pred, const L* __restrict__ label, const uint8_t* __restrict__ lut,
+                  unsigned long long* __restrict__ hist, int ignore, int* err_flag) {
+  const int Y = blockIdx.y * kEvTile + (threadIdx.x >> 4), X = blockIdx.x * kEvTile + (threadIdx.x & 15);
+  if (Y >= H || X >= W) return;
+  const int64_t p = (int64_t)Y * W + X, HW = (int64_t)H * W;
+  float best = -FLT_MAX;
+  int arg = 0;
+  for (int c0 = 0; c0 < C; c0 += kEvCB) {
+    float P[kEvCB];
+#pragma unroll
+    for (int i = 0; i < kEvCB; ++i) P[i] = 0.f;
+    const int nc = (C - c0) < kEvCB ? (C - c0) : kEvCB;
+    for (int s = 0; s < ps.n; ++s) {
+      const EvalPassDev& ep = ps.p[s];
+      const EvalPixel<T> px = eval_pixel<T>(ep, Y, X);
+      const int64_t hw = (int64_t)ep.h * ep.w;
+      const float2 st = stats[(int64_t)s * HW + p];
+      if (nc == kEvCB) {
+        float z[kEvCB];
+#pragma unroll
+        for (int i = 0; i < kEvCB; ++i) z[i] = px.at((int64_t)(c0 + i) * hw);
+#pragma unroll
+        for (int i = 0; i < kEvCB; ++i) P[i] += ex2_approx((z[i] - st.x) * kLog2e) * st.y;
+      } else {
+#pragma unroll
+        for (int i = 0; i < kEvCB; ++i)
+          if (i < nc) P[i] += ex2_approx((px.at((int64_t)(c0 + i) * hw) - st.x) * kLog2e) * st.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kEvCB; ++i)
+      if (i < nc && (P[i] > best || (c0 + i) == 0)) { best = P[i]; arg = c0 + i; }
+  }
+  if (pred) pred[p] = arg;
+  if (hist) {
+    int l = load_label<L>(label, p);
+    if (lut) l = ((unsigned)l < 256u) ? (int)__ldg(lut + l) : -1;
+    if (l != ignore) {
+      if ((unsigned)l >= (unsigned)C) { if (err_flag) atomicOr(err_flag, MDSEG_ERR_LABEL_RANGE); }
+      else atomicAdd(&hist[(int64_t)l * C + arg], 1ull);
+    }
   }
 }
 
@@ -193,4 +335,66 @@ extern "C" int mdseg_label_nearest(const void* in, int dtype, int Hin, int Win, 
   }
   MDSEG_LAUNCH_OK();
   return 0;
+}
+
+namespace mdseg {
+namespace {
+template <typename T>
+int launch_eval_fused(const EvalPassesDev& ps, int C, int H, int W, float2* stats, int64_t* pred, const void* label,
+                      int label_dtype, const uint8_t* lut, int64_t* hist, int ignore, int32_t* ef, cudaStream_t s) {
+  const dim3 grid((unsigned)((W + kEvTile - 1) / kEvTile), (unsigned)((H + kEvTile - 1) / kEvTile));
+  eval_stats_kernel<T><<<dim3(grid.x, grid.y, (unsigned)ps.n), kEvThreads, 0, s>>>(ps, C, H, W, stats);
+  MDSEG_LAUNCH_OK();
+#define MDSEG_EVF(LT)                                                                                          \
+  eval_fused_kernel<T, LT><<<grid, kEvThreads, 0, s>>>(ps, C, H, W, stats, (long long*)pred, (const LT*)label, lut, \
+                                                       (unsigned long long*)hist, ignore, ef)
+  switch (hist ? label_dtype : MDSEG_U8) {
+    case MDSEG_U8: MDSEG_EVF(uint8_t); break;
+    case MDSEG_I32: MDSEG_EVF(int32_t); break;
+    case MDSEG_I64: MDSEG_EVF(int64_t); break;
+    default: set_error("mdseg_eval_fused: unsupported label dtype %d", label_dtype); return 2;
+  }
+#undef MDSEG_EVF
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+}  // namespace
+}  // namespace mdseg
+
+extern "C" size_t mdseg_eval_fused_workspace_bytes(int n_passes, int H, int W) {
+  if (n_passes <= 0 || H <= 0 || W <= 0) return 256;
+  return (size_t)n_passes * H * W * 8 + 256;
+}
+
+extern "C" int mdseg_eval_fused(const mdseg_eval_passes* passes, int C, int H, int W, int64_t* pred, const void* label,
+                                int label_dtype, const uint8_t* lut256, int64_t* hist, int ignore, void* workspace,
+                                size_t workspace_bytes, int32_t* err_flag, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(passes && passes->n_passes > 0 && passes->n_passes <= MDSEG_MAX_EVAL_PASSES,
+                "mdseg_eval_fused: 1..%d passes", MDSEG_MAX_EVAL_PASSES);
+  MDSEG_REQUIRE(C > 0 && H > 0 && W > 0 && H <= 65535 * kEvTile && (int64_t)C * C < (1LL << 31),
+                "mdseg_eval_fused: bad shape");
+  MDSEG_REQUIRE(pred || hist, "mdseg_eval_fused: nothing to compute (pred and hist are NULL)");
+  MDSEG_REQUIRE(!hist || (label && err_flag), "mdseg_eval_fused: hist needs label and err_flag");
+  MDSEG_REQUIRE(is_float_dtype(passes->dtype), "mdseg_eval_fused: unsupported dtype %d", passes->dtype);
+  MDSEG_REQUIRE(workspace && workspace_bytes >= mdseg_eval_fused_workspace_bytes(passes->n_passes, H, W),
+                "mdseg_eval_fused: workspace too small");
+  EvalPassesDev ps;
+  ps.n = passes->n_passes;
+  for (int i = 0; i < ps.n; ++i) {
+    const mdseg_eval_pass& e = passes->p[i];
+    MDSEG_REQUIRE(e.logits && e.h > 0 && e.w > 0, "mdseg_eval_fused: bad pass %d", i);
+    ps.p[i].logits = e.logits;
+    ps.p[i].ym = AxisMap{axis_scale(e.h, H), e.h};
+    ps.p[i].xm = AxisMap{axis_scale(e.w, W), e.w};
+    ps.p[i].h = e.h; ps.p[i].w = e.w; ps.p[i].flip = e.flip;
+  }
+  float2* stats = reinterpret_cast<float2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (passes->dtype) {
+    case MDSEG_F32: return launch_eval_fused<float>(ps, C, H, W, stats, pred, label, label_dtype, lut256, hist, ignore, err_flag, s);
+    case MDSEG_BF16: return launch_eval_fused<__nv_bfloat16>(ps, C, H, W, stats, pred, label, label_dtype, lut256, hist, ignore, err_flag, s);
+    case MDSEG_F16: return launch_eval_fused<__half>(ps, C, H, W, stats, pred, label, label_dtype, lut256, hist, ignore, err_flag, s);
+  }
+  return 2;
 }

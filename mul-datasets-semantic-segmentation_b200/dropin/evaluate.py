@@ -2,9 +2,10 @@
 
 ``MscEvalV0(scales, flip, ignore_label)(net, dl, n_classes, dataset_id) -> float`` keeps the reference
 signature.  Per image the reference up-samples every (scale, flip) pass to label size, soft-maxes, sums,
-arg-maxes, copies label and prediction to the host and calls ``np.bincount``; here each pass is one fused
-upsample+softmax+accumulate kernel, the arg-max and the confusion matrix are one more, the accumulator is an
-exact int64 matrix on the device, and the only collective is one all-reduce of that matrix.
+arg-maxes, copies label and prediction to the host and calls ``np.bincount``; here all passes of an image go
+through two kernels that keep the probability accumulators in registers, take the arg-max and update an
+exact int64 confusion matrix on the device (``ops.eval_fused``; more than 16 passes or mixed dtypes fall
+back to one upsample+softmax+accumulate kernel per pass), and the only collective is one all-reduce of that matrix.
 """
 import math
 
@@ -31,6 +32,11 @@ class SegHist:
     def update_from_passes(self, label, passes):
         """label [H, W]; passes: iterable of (logits [C, h, w], flip) — evaluate.py:64-93 for one image."""
         H, W = label.shape[-2:]
+        passes = list(passes)
+        if ops.eval_fused_fits(self.n_classes, len(passes)) and len({p[0].dtype for p in passes}) == 1:
+            # every pass of the image at once, no [C, H, W] probability tensor
+            return ops.eval_fused(passes, (H, W), label=label.reshape(H, W), hist=self.hist, lut=self.lb_map,
+                                  ignore=self.ignore_label)[0]
         probs = torch.empty(self.n_classes, H, W, dtype=torch.float32, device=label.device)
         first = True
         for logits, flip in passes:

@@ -54,6 +54,17 @@ class HistTable(C.Structure):
     _fields_ = [("n_datasets", C.c_int), ("C", C.c_int * MAX_DATASETS), ("offset", C.c_longlong * MAX_DATASETS)]
 
 
+MAX_EVAL_PASSES = 16
+
+
+class EvalPass(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("h", C.c_int), ("w", C.c_int), ("flip", C.c_int), ("reserved", C.c_int)]
+
+
+class EvalPasses(C.Structure):
+    _fields_ = [("p", EvalPass * MAX_EVAL_PASSES), ("n_passes", C.c_int), ("dtype", C.c_int)]
+
+
 class GraphTable(C.Structure):
     _fields_ = [("g", SparseGraph * MAX_DATASETS), ("n_datasets", C.c_int), ("C_uni", C.c_int)]
 
@@ -93,6 +104,8 @@ SIGNATURES = {
                                     C.POINTER(SrcTable), _P, C.c_size_t, _P]),
     "mdseg_add_planes": (_I, [_P, _P, _P, _I, _L, _P]),
     "mdseg_eval_accum": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P]),
+    "mdseg_eval_fused_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "mdseg_eval_fused": (_I, [C.POINTER(EvalPasses), _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, C.c_size_t, _P, _P]),
     "mdseg_argmax_hist": (_I, [_P, _I, _L, _P, _P, _I, _P, _P, _I, _P, _P]),
     "mdseg_label_nearest": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),
 }

@@ -696,6 +696,59 @@ def eval_accum(logits, probs, flip=False, first=False):
     return probs
 
 
+def eval_fused(passes, size, label=None, hist=None, lut=None, ignore=255, want_pred=True):
+    """All (scale, flip) passes of one image in one kernel (evaluate.py:136-181): pred = argmax_c of the summed
+    soft-max of every up-sampled pass, hist[label, pred] += 1.  passes: [(logits [C, h, w], flip), ...] of one
+    float dtype; size = (H, W) of the label.  Returns (pred or None, hist or None).  At most 16 passes (see
+    eval_fused_fits)."""
+    H, W = int(size[0]), int(size[1])
+    tab = N.EvalPasses()
+    keep = []
+    dt = None
+    for i, (lg, flip) in enumerate(passes):
+        _require_cuda(lg)
+        if lg.dim() == 4:
+            if lg.shape[0] != 1:
+                raise ValueError("eval_fused takes one image")
+            lg = lg[0]
+        if lg.dtype not in _DT or _DT[lg.dtype] > N.F16:
+            lg = lg.float()
+        lg = lg.contiguous()
+        dt = lg.dtype if dt is None else dt
+        if lg.dtype != dt:
+            raise TypeError("eval_fused: all passes must share one dtype")
+        if i == 0:
+            Cc = lg.shape[0]
+        elif lg.shape[0] != Cc:
+            raise ValueError("eval_fused: all passes must share the class count")
+        keep.append(lg)
+        tab.p[i].logits, tab.p[i].h, tab.p[i].w, tab.p[i].flip = lg.data_ptr(), lg.shape[1], lg.shape[2], int(bool(flip))
+    if not keep:
+        raise ValueError("eval_fused: no passes")
+    tab.n_passes, tab.dtype = len(keep), _DT[dt]
+    dev = keep[0].device
+    pred = torch.empty(H, W, dtype=torch.int64, device=dev) if want_pred else None
+    lab = None
+    if label is not None:
+        lab = _labels(label)
+        if lab.numel() != H * W:
+            raise ValueError("label size mismatch")
+        if hist is None:
+            hist = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
+    if lut is not None:
+        lut = torch.as_tensor(lut).to(device=dev, dtype=torch.uint8).contiguous()
+    nbytes = N.lib.mdseg_eval_fused_workspace_bytes(len(keep), H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    N.call("mdseg_eval_fused", C.byref(tab), Cc, H, W, _ptr(pred), _ptr(lab), _DT[lab.dtype] if lab is not None else N.U8,
+           _ptr(lut), _ptr(hist) if lab is not None else None, int(ignore), _ptr(ws), nbytes, _ptr(err_flag(dev)),
+           _stream())
+    return pred, hist
+
+
+def eval_fused_fits(n_classes, n_passes):
+    return 0 < n_passes <= N.MAX_EVAL_PASSES
+
+
 def argmax_hist(probs, label=None, hist=None, lut=None, ignore=255, want_pred=True):
     """pred = argmax_c probs; optionally hist[label, pred] += 1 in the same pass (evaluate.py:172-181)."""
     _require_cuda(probs)

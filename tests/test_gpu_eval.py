@@ -68,3 +68,71 @@ def test_wide_class_count_uses_global_histogram(ops):
     hist = torch.zeros(C, C, dtype=torch.int64, device=DEV)
     pred = ops.argmax_hist(probs, label, hist)
     assert np.array_equal(hist.cpu().numpy(), ls.confusion(label.cpu().numpy(), pred.cpu().numpy(), C))
+
+
+@pytest.mark.parametrize("C,H,W", [(19, 96, 160), (150, 70, 90), (7, 33, 17)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("lab_dt", [torch.int64, torch.uint8])
+def test_eval_fused_equals_pass_by_pass(ops, C, H, W, dt, lab_dt):
+    """mdseg_eval_fused (all passes in one kernel, accumulator in shared memory) == mdseg_eval_accum pass by pass +
+    mdseg_argmax_hist, bit for bit: predictions and confusion matrix; ragged tiles, flips, a same-size pass."""
+    g = torch.Generator().manual_seed(C + H)
+    sizes = [(max(2, H // 8), max(2, W // 8)), (H // 4, W // 4), (H // 3 + 1, W // 3 + 2), (H // 4, W // 4), (H, W)]
+    flips = [False, True, False, True, True]
+    passes = [((torch.randn(C, h, w, generator=g) * 3).to(dt).to(DEV), f) for (h, w), f in zip(sizes, flips)]
+    label = torch.randint(0, C, (H, W), generator=g)
+    label[torch.rand(H, W, generator=g) < 0.1] = 255
+    label = label.to(lab_dt).to(DEV)
+    probs = torch.empty(C, H, W, device=DEV)
+    for i, (lg, fl) in enumerate(passes):
+        ops.eval_accum(lg, probs, flip=fl, first=(i == 0))
+    hist_ref = torch.zeros(C, C, dtype=torch.int64, device=DEV)
+    pred_ref = ops.argmax_hist(probs, label, hist_ref)
+    hist = torch.zeros(C, C, dtype=torch.int64, device=DEV)
+    hist[0, 0] = 3  # accumulate-into semantics
+    pred, _ = ops.eval_fused(passes, (H, W), label=label, hist=hist)
+    hist[0, 0] -= 3
+    assert torch.equal(pred, pred_ref)
+    assert torch.equal(hist, hist_ref)
+    assert np.array_equal(hist.cpu().numpy(), ls.confusion(label.cpu().numpy().astype(np.int64), pred.cpu().numpy(), C))
+    only_pred, none_hist = ops.eval_fused(passes, (H, W))
+    assert none_hist is None and torch.equal(only_pred, pred_ref)
+    ops.check_errors(DEV)
+
+
+def test_eval_fused_against_reference_probabilities(ops):
+    """Against the reference op sequence (interpolate -> softmax -> sum -> argmax, evaluate.py:149-172) on the CPU:
+    identical predictions wherever the top-2 gap is above fp32 noise; LUT-fused raw labels."""
+    g = torch.Generator().manual_seed(5)
+    C, H, W = 19, 96, 160
+    sizes = [(12, 20), (24, 40), (32, 56), (24, 40)]
+    flips = [False, True, False, True]
+    passes = [torch.randn(1, C, h, w, generator=g) * 3 for (h, w) in sizes]
+    want_probs = tr.eval_probs(passes, (H, W), flips)
+    raw = torch.randint(0, 34, (H, W), generator=g).to(torch.uint8)
+    lut = np.full(256, 255, dtype=np.uint8)
+    lut[:34] = np.random.default_rng(0).integers(0, C, 34)
+    lut[5] = 255
+    pred, hist = ops.eval_fused([(p.to(DEV), f) for p, f in zip(passes, flips)], (H, W), label=raw.to(DEV), lut=lut)
+    ref_pred = tr.eval_preds(want_probs)[0]
+    top2 = want_probs[0].topk(2, dim=0).values
+    clear = (top2[0] - top2[1]) > 1e-5
+    assert torch.equal(pred.cpu()[clear], ref_pred[clear]) and clear.float().mean() > 0.999
+    assert np.array_equal(hist.cpu().numpy(), ls.confusion(ls.lut_gather(raw.numpy(), lut), pred.cpu().numpy(), C))
+    ops.check_errors(DEV)
+
+
+def test_dropin_evaluator_takes_the_fused_route(ops):
+    from mdseg_b200.dropin.evaluate import SegHist
+    g = torch.Generator().manual_seed(9)
+    C, H, W = 12, 64, 96
+    passes = [(torch.randn(C, 16, 24, generator=g).to(DEV), False), (torch.randn(C, 24, 40, generator=g).to(DEV), True)]
+    label = torch.randint(0, C, (H, W), generator=g).to(DEV)
+    acc = SegHist(C, torch.device(DEV))
+    pred = acc.update_from_passes(label, passes)
+    probs = torch.empty(C, H, W, device=DEV)
+    for i, (lg, fl) in enumerate(passes):
+        ops.eval_accum(lg, probs, flip=fl, first=(i == 0))
+    want = torch.zeros(C, C, dtype=torch.int64, device=DEV)
+    want_pred = ops.argmax_hist(probs, label, want)
+    assert torch.equal(pred, want_pred) and torch.equal(acc.hist, want)
