@@ -28,9 +28,26 @@ template <typename T> struct EvalPixel {
 };
 constexpr int kEvBlk = 8;  // classes per block: 32 independent loads in flight per thread
 
-// Soft-max statistics of the pixel over C classes (class stride hw): the running maximum is updated once per
-// block of eight classes, so a block costs nine exponentials and its 32 loads are independent.  Both evaluator
-// kernels use this function and the same block order, which is what makes their sums bit-identical.
+// Soft-max statistics of a pixel: the running maximum is updated once per block of eight classes, so a block
+// costs nine exponentials and its loads are independent.  Every evaluator kernel feeds the classes through these
+// two functions in the same order (blocks of eight from class 0 while they fit, then single classes), which is
+// what makes their sums bit-identical.
+__device__ __forceinline__ void stats_feed8(const float (&z)[kEvBlk], float& m, float& sum) {
+  float mb = z[0];
+#pragma unroll
+  for (int i = 1; i < kEvBlk; ++i) mb = fmaxf(mb, z[i]);
+  const float mn = fmaxf(m, mb);
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEvBlk; ++i) part += ex2_approx((z[i] - mn) * kLog2e);
+  sum = sum * ex2_approx((m - mn) * kLog2e) + part;
+  m = mn;
+}
+__device__ __forceinline__ void stats_feed1(float z, float& m, float& sum) {
+  const float mn = fmaxf(m, z);
+  sum = sum * ex2_approx((m - mn) * kLog2e) + ex2_approx((z - mn) * kLog2e);
+  m = mn;
+}
 template <typename T>
 __device__ __forceinline__ void eval_softmax_stats(const EvalPixel<T>& px, int C, int64_t hw, float& m, float& inv) {
   m = -FLT_MAX;
@@ -40,22 +57,9 @@ __device__ __forceinline__ void eval_softmax_stats(const EvalPixel<T>& px, int C
     float z[kEvBlk];
 #pragma unroll
     for (int i = 0; i < kEvBlk; ++i) z[i] = px.at((int64_t)(c + i) * hw);
-    float mb = z[0];
-#pragma unroll
-    for (int i = 1; i < kEvBlk; ++i) mb = fmaxf(mb, z[i]);
-    const float mn = fmaxf(m, mb);
-    float part = 0.f;
-#pragma unroll
-    for (int i = 0; i < kEvBlk; ++i) part += ex2_approx((z[i] - mn) * kLog2e);
-    sum = sum * ex2_approx((m - mn) * kLog2e) + part;
-    m = mn;
+    stats_feed8(z, m, sum);
   }
-  for (; c < C; ++c) {
-    const float z = px.at((int64_t)c * hw);
-    const float mn = fmaxf(m, z);
-    sum = sum * ex2_approx((m - mn) * kLog2e) + ex2_approx((z - mn) * kLog2e);
-    m = mn;
-  }
+  for (; c < C; ++c) stats_feed1(px.at((int64_t)c * hw), m, sum);
   inv = 1.0f / sum;
 }
 
@@ -233,6 +237,147 @@ eval_fused_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H, int W,
   }
 }
 
+// ---- the same two kernels with the low-resolution patch of a tile staged in shared memory -------------------
+// For passes that do not down-sample (h <= H, w <= W) the 16 x 16 label tile of a CTA interpolates inside a
+// patch of at most 17 x 17 logits per class.  The direct kernels fetch each corner from L1 / L2 (four lookups per
+// pixel, class and pass — the L1 tag stage is what binds them); here the CTA copies the patch of 16 classes once
+// (one or two elements per thread and class, double-buffered, one barrier per block) and the corners come from
+// shared memory, mostly as broadcasts.
+constexpr int kEvPatch = 18;
+constexpr int kEvPatchElems = kEvPatch * kEvPatch;
+
+struct EvalPatch {
+  int o00, o01, o10, o11;      // this thread's corners inside the patch of one class
+  float l0h, l1h, l0w, l1w;
+  int e[2];                    // patch elements this thread copies (-1: none) ...
+  int64_t src[2];              // ... and their offsets inside a class plane
+  __device__ __forceinline__ float at(const float* pc) const {
+    return l0h * (l0w * pc[o00] + l1w * pc[o01]) + l1h * (l0w * pc[o10] + l1w * pc[o11]);
+  }
+};
+
+__device__ __forceinline__ EvalPatch eval_patch(const EvalPassDev& ep, int Y, int X, int H, int W) {
+  const int Yt0 = blockIdx.y * kEvTile, Xt0 = blockIdx.x * kEvTile;
+  const int Yl = min(Yt0 + kEvTile - 1, H - 1), Xl = min(Xt0 + kEvTile - 1, W - 1);
+  const int r0 = ep.ym.floor_at(Yt0), r1 = min(ep.h - 1, ep.ym.floor_at(Yl) + 1);
+  const int c0 = ep.xm.floor_at(Xt0), c1 = min(ep.w - 1, ep.xm.floor_at(Xl) + 1);
+  const int n_rows = r1 - r0 + 1, n_cols = c1 - c0 + 1;
+  EvalPatch g;
+  int y0, y1, x0, x1;
+  ep.ym.at(Y, y0, y1, g.l0h, g.l1h);
+  ep.xm.at(X, x0, x1, g.l0w, g.l1w);
+  g.o00 = (y0 - r0) * n_cols + (x0 - c0); g.o01 = (y0 - r0) * n_cols + (x1 - c0);
+  g.o10 = (y1 - r0) * n_cols + (x0 - c0); g.o11 = (y1 - r0) * n_cols + (x1 - c0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int e = threadIdx.x + k * kEvThreads;
+    g.e[k] = -1;
+    g.src[k] = 0;
+    if (e < n_rows * n_cols) {
+      const int ry = e / n_cols, rx = e - ry * n_cols;
+      const int sx = ep.flip ? ep.w - 1 - (c0 + rx) : c0 + rx;  // torch.flip(logits, dims=(3,)) before interpolate
+      g.e[k] = e;
+      g.src[k] = (int64_t)(r0 + ry) * ep.w + sx;
+    }
+  }
+  return g;
+}
+
+// copy the patch of classes [c0, c0 + nc) of one pass into `buf` ([kEvCB][kEvPatchElems])
+template <typename T>
+__device__ __forceinline__ void eval_stage(const EvalPassDev& ep, const EvalPatch& g, int c0, int nc, float* buf) {
+  const T* base = (const T*)ep.logits + (int64_t)c0 * ep.h * ep.w;
+  const int64_t hw = (int64_t)ep.h * ep.w;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (g.e[k] >= 0) {
+      float v[kEvCB];
+#pragma unroll
+      for (int i = 0; i < kEvCB; ++i) v[i] = (i < nc) ? to_f32<T>(base[(int64_t)i * hw + g.src[k]]) : 0.f;
+#pragma unroll
+      for (int i = 0; i < kEvCB; ++i) buf[i * kEvPatchElems + g.e[k]] = v[i];
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEvThreads)
+eval_stats_staged_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H, int W, float2* __restrict__ stats) {
+  __shared__ float patch[2][kEvCB * kEvPatchElems];
+  const int Yr = blockIdx.y * kEvTile + (threadIdx.x >> 4), Xr = blockIdx.x * kEvTile + (threadIdx.x & 15);
+  const bool inside = Yr < H && Xr < W;
+  const int Y = min(Yr, H - 1), X = min(Xr, W - 1);  // threads outside the image still help with the copies
+  const int s = blockIdx.z;
+  const EvalPassDev& ep = ps.p[s];
+  const EvalPatch g = eval_patch(ep, Y, X, H, W);
+  float m = -FLT_MAX, sum = 0.f;
+  int it = 0;
+  for (int c0 = 0; c0 < C; c0 += kEvCB, ++it) {
+    const int nc = (C - c0) < kEvCB ? (C - c0) : kEvCB;
+    float* buf = patch[it & 1];
+    eval_stage<T>(ep, g, c0, nc, buf);
+    __syncthreads();
+#pragma unroll
+    for (int hb = 0; hb < kEvCB / kEvBlk; ++hb) {
+      const int cb = c0 + hb * kEvBlk;
+      if (cb + kEvBlk <= C) {
+        float z[kEvBlk];
+#pragma unroll
+        for (int i = 0; i < kEvBlk; ++i) z[i] = g.at(buf + (hb * kEvBlk + i) * kEvPatchElems);
+        stats_feed8(z, m, sum);
+      } else {
+        for (int c = cb; c < C && c < cb + kEvBlk; ++c) stats_feed1(g.at(buf + (c - c0) * kEvPatchElems), m, sum);
+      }
+    }
+  }
+  if (inside) stats[((int64_t)s * H + Y) * W + X] = make_float2(m, 1.0f / sum);
+}
+
+template <typename T, typename L>
+__global__ void __launch_bounds__(kEvThreads)
+eval_fused_staged_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H, int W,
+                         const float2* __restrict__ stats, long long* __restrict__ pred, const L* __restrict__ label,
+                         const uint8_t* __restrict__ lut, unsigned long long* __restrict__ hist, int ignore,
+                         int* err_flag) {
+  __shared__ float patch[2][kEvCB * kEvPatchElems];
+  const int Yr = blockIdx.y * kEvTile + (threadIdx.x >> 4), Xr = blockIdx.x * kEvTile + (threadIdx.x & 15);
+  const bool inside = Yr < H && Xr < W;
+  const int Y = min(Yr, H - 1), X = min(Xr, W - 1);
+  const int64_t p = (int64_t)Y * W + X, HW = (int64_t)H * W;
+  float best = -FLT_MAX;
+  int arg = 0, it = 0;
+  for (int c0 = 0; c0 < C; c0 += kEvCB) {
+    float P[kEvCB];
+#pragma unroll
+    for (int i = 0; i < kEvCB; ++i) P[i] = 0.f;
+    const int nc = (C - c0) < kEvCB ? (C - c0) : kEvCB;
+    for (int s = 0; s < ps.n; ++s, ++it) {
+      const EvalPassDev& ep = ps.p[s];
+      const EvalPatch g = eval_patch(ep, Y, X, H, W);
+      float* buf = patch[it & 1];
+      eval_stage<T>(ep, g, c0, nc, buf);
+      const float2 st = stats[(int64_t)s * HW + p];
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kEvCB; ++i)
+        if (i < nc) P[i] += ex2_approx((g.at(buf + i * kEvPatchElems) - st.x) * kLog2e) * st.y;
+    }
+#pragma unroll
+    for (int i = 0; i < kEvCB; ++i)
+      if (i < nc && (P[i] > best || (c0 + i) == 0)) { best = P[i]; arg = c0 + i; }
+  }
+  if (!inside) return;
+  if (pred) pred[p] = arg;
+  if (hist) {
+    int l = load_label<L>(label, p);
+    if (lut) l = ((unsigned)l < 256u) ? (int)__ldg(lut + l) : -1;
+    if (l != ignore) {
+      if ((unsigned)l >= (unsigned)C) { if (err_flag) atomicOr(err_flag, MDSEG_ERR_LABEL_RANGE); }
+      else atomicAdd(&hist[(int64_t)l * C + arg], 1ull);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 label_nearest_kernel(const T* __restrict__ in, int Hin, int Win, T* __restrict__ out, int Hout, int Wout, int n,
@@ -343,11 +488,21 @@ template <typename T>
 int launch_eval_fused(const EvalPassesDev& ps, int C, int H, int W, float2* stats, int64_t* pred, const void* label,
                       int label_dtype, const uint8_t* lut, int64_t* hist, int ignore, int32_t* ef, cudaStream_t s) {
   const dim3 grid((unsigned)((W + kEvTile - 1) / kEvTile), (unsigned)((H + kEvTile - 1) / kEvTile));
-  eval_stats_kernel<T><<<dim3(grid.x, grid.y, (unsigned)ps.n), kEvThreads, 0, s>>>(ps, C, H, W, stats);
+  bool staged = true;  // every pass up-samples: a tile's patch has at most 17 x 17 logits per class
+  for (int i = 0; i < ps.n; ++i) staged = staged && ps.p[i].h <= H && ps.p[i].w <= W;
+  if (staged) eval_stats_staged_kernel<T><<<dim3(grid.x, grid.y, (unsigned)ps.n), kEvThreads, 0, s>>>(ps, C, H, W, stats);
+  else eval_stats_kernel<T><<<dim3(grid.x, grid.y, (unsigned)ps.n), kEvThreads, 0, s>>>(ps, C, H, W, stats);
   MDSEG_LAUNCH_OK();
-#define MDSEG_EVF(LT)                                                                                          \
-  eval_fused_kernel<T, LT><<<grid, kEvThreads, 0, s>>>(ps, C, H, W, stats, (long long*)pred, (const LT*)label, lut, \
-                                                       (unsigned long long*)hist, ignore, ef)
+#define MDSEG_EVF(LT)                                                                                              \
+  do {                                                                                                             \
+    if (staged)                                                                                                    \
+      eval_fused_staged_kernel<T, LT><<<grid, kEvThreads, 0, s>>>(ps, C, H, W, stats, (long long*)pred,            \
+                                                                  (const LT*)label, lut, (unsigned long long*)hist, \
+                                                                  ignore, ef);                                     \
+    else                                                                                                           \
+      eval_fused_kernel<T, LT><<<grid, kEvThreads, 0, s>>>(ps, C, H, W, stats, (long long*)pred, (const LT*)label, \
+                                                           lut, (unsigned long long*)hist, ignore, ef);            \
+  } while (0)
   switch (hist ? label_dtype : MDSEG_U8) {
     case MDSEG_U8: MDSEG_EVF(uint8_t); break;
     case MDSEG_I32: MDSEG_EVF(int32_t); break;

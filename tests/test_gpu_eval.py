@@ -136,3 +136,18 @@ def test_dropin_evaluator_takes_the_fused_route(ops):
     want = torch.zeros(C, C, dtype=torch.int64, device=DEV)
     want_pred = ops.argmax_hist(probs, label, want)
     assert torch.equal(pred, want_pred) and torch.equal(acc.hist, want)
+
+
+def test_eval_fused_with_a_downsampling_pass_takes_the_direct_kernels(ops):
+    """A pass larger than the label (scale > stride) cannot use the staged 17 x 17 patches: direct-load kernels."""
+    g = torch.Generator().manual_seed(21)
+    C, H, W = 23, 40, 56
+    passes = [(torch.randn(C, 10, 14, generator=g).to(DEV), False), (torch.randn(C, 50, 70, generator=g).to(DEV), True)]
+    label = torch.randint(0, C, (H, W), generator=g).to(DEV)
+    probs = torch.empty(C, H, W, device=DEV)
+    for i, (lg, fl) in enumerate(passes):
+        ops.eval_accum(lg, probs, flip=fl, first=(i == 0))
+    want = torch.zeros(C, C, dtype=torch.int64, device=DEV)
+    want_pred = ops.argmax_hist(probs, label, want)
+    pred, hist = ops.eval_fused(passes, (H, W), label=label)
+    assert torch.equal(pred, want_pred) and torch.equal(hist, want)
