@@ -424,7 +424,7 @@ def cpu_step(bt):
     for d, s, e in dataset_slices(ids):
         h = ls.confusion(labels[s:e].numpy(), bt["pred"][s:e].numpy(), bt["n_cats"][d])
         mious.append(ls.ious_miou(h)[1])
-    return float(loss), mious
+    return float(loss.detach()), mious
 
 
 def run_eager_gpu(args, local_rank):
@@ -472,7 +472,9 @@ def run_eager_gpu(args, local_rank):
 def cpu_sample_images(workload):
     ids = WORKLOADS[workload][2]
     if workload in ("cfg3", "cfg2"):
-        return [0, len(ids) // 2]  # two full-resolution images from two different datasets
+        # one full-resolution image of EVERY dataset: the sample's mean class count (cfg3: 64) matches the
+        # batch's (61.2), so pixels/s of the sample is representative of the whole batch
+        return [ids.index(d) for d in sorted(set(ids))]
     return list(range(len(ids)))
 
 
