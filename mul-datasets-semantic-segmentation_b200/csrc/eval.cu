@@ -40,13 +40,18 @@ __device__ __forceinline__ void stats_feed8(const float (&z)[kEvBlk], float& m, 
   float part = 0.f;
 #pragma unroll
   for (int i = 0; i < kEvBlk; ++i) part += ex2_approx((z[i] - mn) * kLog2e);
-  sum = sum * ex2_approx((m - mn) * kLog2e) + part;
+  sum = fmaf(sum, ex2_approx((m - mn) * kLog2e), part);
   m = mn;
 }
 __device__ __forceinline__ void stats_feed1(float z, float& m, float& sum) {
   const float mn = fmaxf(m, z);
-  sum = sum * ex2_approx((m - mn) * kLog2e) + ex2_approx((z - mn) * kLog2e);
+  sum = fmaf(sum, ex2_approx((m - mn) * kLog2e), ex2_approx((z - mn) * kLog2e));
   m = mn;
+}
+// probability of one class given the pixel's statistics, added to an accumulator (the subtraction is exact for
+// nearby values, which a fused z * log2e - max * log2e would not be)
+__device__ __forceinline__ float eval_add_prob(float acc, float z, float m, float inv) {
+  return fmaf(ex2_approx((z - m) * kLog2e), inv, acc);
 }
 template <typename T>
 __device__ __forceinline__ void eval_softmax_stats(const EvalPixel<T>& px, int C, int64_t hw, float& m, float& inv) {
@@ -88,15 +93,13 @@ eval_accum_kernel(const T* __restrict__ logits, int C, int h, int w, float* __re
       for (int i = 0; i < kEvBlk; ++i) z[i] = px.at((int64_t)(c + i) * hw);
 #pragma unroll
       for (int i = 0; i < kEvBlk; ++i) {
-        const float pr = ex2_approx((z[i] - m) * kLog2e) * inv;
         float* dst = probs + (int64_t)(c + i) * HW + p;
-        *dst = first ? pr : (*dst + pr);
+        *dst = eval_add_prob(first ? 0.f : *dst, z[i], m, inv);
       }
     }
     for (; c < C; ++c) {
-      const float pr = ex2_approx((px.at((int64_t)c * hw) - m) * kLog2e) * inv;
       float* dst = probs + (int64_t)c * HW + p;
-      *dst = first ? pr : (*dst + pr);
+      *dst = eval_add_prob(first ? 0.f : *dst, px.at((int64_t)c * hw), m, inv);
     }
   }
 }
@@ -215,11 +218,11 @@ eval_fused_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H, int W,
 #pragma unroll
         for (int i = 0; i < kEvCB; ++i) z[i] = px.at((int64_t)(c0 + i) * hw);
 #pragma unroll
-        for (int i = 0; i < kEvCB; ++i) P[i] += ex2_approx((z[i] - st.x) * kLog2e) * st.y;
+        for (int i = 0; i < kEvCB; ++i) P[i] = eval_add_prob(P[i], z[i], st.x, st.y);
       } else {
 #pragma unroll
         for (int i = 0; i < kEvCB; ++i)
-          if (i < nc) P[i] += ex2_approx((px.at((int64_t)(c0 + i) * hw) - st.x) * kLog2e) * st.y;
+          if (i < nc) P[i] = eval_add_prob(P[i], px.at((int64_t)(c0 + i) * hw), st.x, st.y);
       }
     }
 #pragma unroll
@@ -360,7 +363,7 @@ eval_fused_staged_kernel(const __grid_constant__ EvalPassesDev ps, int C, int H,
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < kEvCB; ++i)
-        if (i < nc) P[i] += ex2_approx((g.at(buf + i * kEvPatchElems) - st.x) * kLog2e) * st.y;
+        if (i < nc) P[i] = eval_add_prob(P[i], g.at(buf + i * kEvPatchElems), st.x, st.y);
     }
 #pragma unroll
     for (int i = 0; i < kEvCB; ++i)
