@@ -91,11 +91,11 @@ eval_accum_kernel(const T* __restrict__ logits, int C, int h, int w, float* __re
       float z[kEvBlk];
 #pragma unroll
       for (int i = 0; i < kEvBlk; ++i) z[i] = px.at((int64_t)(c + i) * hw);
+      float acc[kEvBlk];
 #pragma unroll
-      for (int i = 0; i < kEvBlk; ++i) {
-        float* dst = probs + (int64_t)(c + i) * HW + p;
-        *dst = eval_add_prob(first ? 0.f : *dst, z[i], m, inv);
-      }
+      for (int i = 0; i < kEvBlk; ++i) acc[i] = first ? 0.f : probs[(int64_t)(c + i) * HW + p];
+#pragma unroll
+      for (int i = 0; i < kEvBlk; ++i) probs[(int64_t)(c + i) * HW + p] = eval_add_prob(acc[i], z[i], m, inv);
     }
     for (; c < C; ++c) {
       float* dst = probs + (int64_t)c * HW + p;
