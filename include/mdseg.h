@@ -156,6 +156,14 @@ int mdseg_sm_count(void);
 int mdseg_lut_remap(const void* in, int in_dtype, void* out, int out_dtype,
                     const uint8_t* lut256, int oob, int64_t n, void* stream);
 
+/* ---- a4: multi-hot label remap ---------------------------------------------
+ * out[p, u] = table[labels[p], u] (bytes 0 / 1; labels outside [0,255] give a zero
+ * row).  table: uint8 [256, C_uni], out: uint8 / bool [n_px, C_uni], 16-byte aligned.
+ * Replaces ClassRemapOneHotLabel.SegRemapping / SingleSegRemappingOneHot
+ * (lib/class_remap.py:239-276): one compare + masked scatter per dataset class. */
+int mdseg_multihot_remap(const void* labels, int label_dtype, const uint8_t* table,
+                         int C_uni, int64_t n_px, uint8_t* out, void* stream);
+
 /* ---- a12: confusion matrix ----------------------------------------------
  * hist[l*Cb + q] += 1 for every p with l = (lut ? lut[label[p]] : label[p])
  * != ignore, q = pred[p].  hist is int64 [Ca*Cb], accumulated into.

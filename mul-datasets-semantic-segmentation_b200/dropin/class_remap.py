@@ -94,3 +94,31 @@ class ClassRemap:
     def ReverseSegRemap(self, preds, dataset_id):
         """Unified-space predictions -> dataset classes; unmapped ids -> 0 (:189-203)."""
         return ops.lut_remap(preds, self._reverse_luts[dataset_id], oob=0)
+
+
+class ClassRemapOneHotLabel(ClassRemap):
+    """Multi-hot variants (class_remap.py:232-276): bool [b, h, w, num_unify_classes], one table gather per call."""
+
+    def __init__(self, configer=None):
+        super().__init__(configer)
+        if self.configer.exists('contrast', 'update_sim_thresh'):
+            self.update_sim_thresh = self.configer.get('contrast', 'update_sim_thresh')
+        self._multi_tables, self._single_tables = [], []
+        for remap in self.remapList:
+            multi = np.zeros((256, self.num_unify_classes), dtype=np.uint8)
+            single = np.zeros((256, self.num_unify_classes), dtype=np.uint8)
+            for k, v in remap.items():
+                if 0 <= int(k) < 256:
+                    multi[int(k), v] = 1
+                    if len(v) == 1:
+                        single[int(k), v[0]] = 1
+            self._multi_tables.append(multi)
+            self._single_tables.append(single)
+
+    def SingleSegRemappingOneHot(self, labels, dataset_id):
+        """Only classes with exactly one unified target are set (:239-258)."""
+        return ops.multihot_remap(labels, self._single_tables[dataset_id])
+
+    def SegRemapping(self, labels, dataset_id):
+        """mask[p, u] = 1 iff u is a target of labels[p] (:260-276)."""
+        return ops.multihot_remap(labels, self._multi_tables[dataset_id])

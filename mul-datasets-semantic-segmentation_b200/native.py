@@ -77,6 +77,7 @@ SIGNATURES = {
     "mdseg_last_error": (C.c_char_p, []),
     "mdseg_sm_count": (_I, []),
     "mdseg_lut_remap": (_I, [_P, _I, _P, _I, _P, _I, _L, _P]),
+    "mdseg_multihot_remap": (_I, [_P, _I, _P, _I, _L, _P, _P]),
     "mdseg_confusion": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _L, _P, _P]),
     "mdseg_miou": (_I, [_P, _I, _P, _P, _P]),
     "mdseg_lut_remap_images": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _L, _P, _P]),

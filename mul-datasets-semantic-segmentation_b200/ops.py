@@ -108,6 +108,20 @@ def lut_remap(x, lut, out_dtype=None, oob=255):
 
 
 # ---- a12 / a13: confusion matrix, mIoU ---------------------------------------------
+def multihot_remap(labels, table):
+    """bool [..., C_uni]: out[p, :] = table[labels[p], :] with a uint8 [256, C_uni] 0/1 table
+    (ClassRemapOneHotLabel.SegRemapping / SingleSegRemappingOneHot, lib/class_remap.py:239-276)."""
+    _require_cuda(labels)
+    lab = _labels(labels)
+    table = torch.as_tensor(table).to(device=lab.device, dtype=torch.uint8).contiguous()
+    if table.dim() != 2 or table.shape[0] != 256:
+        raise ValueError("table must be [256, C_uni]")
+    Cu = table.shape[1]
+    out = torch.empty(tuple(lab.shape) + (Cu,), dtype=torch.bool, device=lab.device)
+    N.call("mdseg_multihot_remap", _ptr(lab), _DT[lab.dtype], _ptr(table), Cu, lab.numel(), _ptr(out), _stream())
+    return out
+
+
 def confusion(label, pred, n_a, n_b=None, lut=None, ignore=255, hist=None):
     """hist[l, p] += 1 for label != ignore (evaluate.py:89-93).  int64 [n_a, n_b], accumulated in place."""
     _require_cuda(label, pred)

@@ -130,6 +130,29 @@ def reverse_seg_lut(remap, dataset_id):
 
 
 # --- evaluator tail -------------------------------------------------------------------------
+def multihot_seg_remapping(labels, remap, num_unify_classes, single_only=False):
+    """lib/class_remap.py:260-276 (SegRemapping of ClassRemapOneHotLabel) and :239-258
+    (SingleSegRemappingOneHot, single_only=True): bool [b, h, w, C_uni], out[labels == k, v] = 1."""
+    labels = np.asarray(labels)
+    out = np.zeros(labels.shape + (num_unify_classes,), dtype=bool)
+    for k, v in remap.items():
+        if single_only and len(v) > 1:
+            continue
+        sel = labels == int(k)
+        for u in v:
+            out[sel, u] = True
+    return out
+
+
+def multihot_table(remap, num_unify_classes, single_only=False):
+    """The same remap as a uint8 [256, C_uni] table: out[p, :] = table[labels[p], :]."""
+    t = np.zeros((256, num_unify_classes), dtype=np.uint8)
+    for k, v in remap.items():
+        if 0 <= int(k) < 256 and not (single_only and len(v) > 1):
+            t[int(k), v] = 1
+    return t
+
+
 def confusion(label, pred, n_a, n_b=None, ignore_label=IGNORE):
     """evaluate.py:89-93 / :174-181 (square) and :631-634, :1738-1741 (rectangular):
     keep = label != ignore; bincount(label[keep]*n_b + pred[keep], minlength=n_a*n_b).reshape(n_a, n_b).

@@ -60,6 +60,43 @@ def test_class_remap_luts_on_device(ops, golden):
             assert np.array_equal(got.cpu().numpy(), z[f"{tag}_d{d}_reverse"])
 
 
+def test_multihot_remap_golden(ops, golden):
+    """ClassRemapOneHotLabel.SegRemapping / SingleSegRemappingOneHot of the REAL reference (golden) through
+    mdseg_multihot_remap."""
+    import json, os
+    z = golden("multihot.npz")
+    root = os.path.dirname(os.path.abspath(__file__))
+    for tag, n_ds in (("test", 2), ("cca", 3)):
+        raw = json.load(open(os.path.join(root, "golden", f"test_{tag}.json")))
+        remaps, _ = ls.parse_class_remap(raw, n_ds)
+        cu = raw["num_unify_classes"]
+        for d in range(n_ds):
+            lb = torch.from_numpy(z[f"{tag}_d{d}_labels"]).to(DEV)
+            got = ops.multihot_remap(lb, ls.multihot_table(remaps[d], cu))
+            assert got.dtype == torch.bool and np.array_equal(got.cpu().numpy(), z[f"{tag}_d{d}_multi"])
+            got = ops.multihot_remap(lb, ls.multihot_table(remaps[d], cu, single_only=True))
+            assert np.array_equal(got.cpu().numpy(), z[f"{tag}_d{d}_single"])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 5, 7), (3, 64, 96)])
+@pytest.mark.parametrize("cu", [4, 46, 358, 500])
+@pytest.mark.parametrize("dt", [torch.int64, torch.uint8, torch.int32])
+def test_multihot_remap_random_tables(ops, shape, cu, dt):
+    """Random 0/1 tables (shared-memory and global-table routes, ragged 16-byte tails), labels with 255 and, for
+    the wide types, values outside [0, 255] (-> zero row)."""
+    rng = np.random.default_rng(cu + shape[1])
+    table = (rng.random((256, cu)) < 0.1).astype(np.uint8)
+    lab = rng.integers(0, 256, shape)
+    x = torch.from_numpy(lab).to(dt).to(DEV)
+    want = table[lab].astype(bool)
+    if dt != torch.uint8 and lab.size > 2:
+        x.view(-1)[0], x.view(-1)[1] = -3, 4000
+        want.reshape(-1, cu)[0] = False
+        want.reshape(-1, cu)[1] = False
+    got = ops.multihot_remap(x, table)
+    assert got.shape == tuple(shape) + (cu,) and np.array_equal(got.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 1000, 262144 + 5])
 @pytest.mark.parametrize("Ca,Cb", [(19, 19), (150, 150), (150, 358), (2, 3), (300, 300)])
 @pytest.mark.parametrize("lab_dt", [torch.int64, torch.uint8])

@@ -64,6 +64,22 @@ def test_class_remap_golden(golden, tag, cfg, n_ds):
     assert np.array_equal(singles, z[f"{tag}_single_lbs"])
 
 
+@pytest.mark.parametrize("tag,cfg,n_ds", [("test", "test_test.json", 2), ("cca", "test_cca.json", 3)])
+def test_multihot_golden(golden, tag, cfg, n_ds):
+    """ClassRemapOneHotLabel.{SegRemapping, SingleSegRemappingOneHot} of the real reference (class_remap.py:239-276):
+    the per-class restatement and the [256, C_uni] table form the kernel consumes."""
+    z = golden("multihot.npz")
+    raw = json.load(open(os.path.join(ROOT, "tests", "golden", cfg)))
+    remaps, _ = ls.parse_class_remap(raw, n_ds)
+    cu = raw["num_unify_classes"]
+    for d in range(n_ds):
+        lb = z[f"{tag}_d{d}_labels"]
+        assert np.array_equal(ls.multihot_seg_remapping(lb, remaps[d], cu), z[f"{tag}_d{d}_multi"])
+        assert np.array_equal(ls.multihot_seg_remapping(lb, remaps[d], cu, single_only=True), z[f"{tag}_d{d}_single"])
+        assert np.array_equal(ls.multihot_table(remaps[d], cu)[lb].astype(bool), z[f"{tag}_d{d}_multi"])
+        assert np.array_equal(ls.multihot_table(remaps[d], cu, single_only=True)[lb].astype(bool), z[f"{tag}_d{d}_single"])
+
+
 @pytest.mark.parametrize("name", ["thresh", "topk", "allign"])
 def test_ohem_golden(golden, name):
     """OhemCELoss(0.7) of the real reference: value, gradient, both branches and the all-ignore NaN."""
