@@ -282,6 +282,15 @@ int mdseg_proj_bwd(const float* dyA, const float* dyB, int y_cmax,
                    const int32_t* dataset_ids, int n_images, int h, int w,
                    void* dx, int dtype, void* stream);
 
+/* The same adjoint with the dense graphs on the tcgen05 tensor cores (K = C_ds, the unified
+ * channels tiled by at most 128 per CTA); precision and envelope as mdseg_proj_fwd_tc, the
+ * remaining datasets and the zero fill go through the kernels of mdseg_proj_bwd. */
+size_t mdseg_proj_bwd_tc_workspace_bytes(const mdseg_graph_table* graphs /*host*/, int dtype);
+int mdseg_proj_bwd_tc(const float* dyA, const float* dyB, int y_cmax,
+                      const mdseg_graph_table* graphs /*host*/, const int32_t* dataset_ids,
+                      int n_images, int h, int w, void* dx, int dtype, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* d bi_graph (GNN stage): dG_d[n, c] += Σ_{b in d} Σ_px (dyA+dyB)[b,n,px] * x[b,c,px]
  * dG: fp32 [n_datasets][dg_stride] with row-major [C_ds, C_uni] inside, must be
  * zeroed by the caller. */

@@ -645,7 +645,8 @@ extern "C" size_t mdseg_mds_bwd_workspace_bytes(const mdseg_src_table* src, cons
     const int n_seg = (h - 1 + sr - 1) / sr;
     return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W * 5 + 1024;
   }
-  return 2 * (size_t)n_images * c_max * h * w * 4 + 256;  // generic route: two gradient planes
+  // generic route: two gradient planes + the converted dense graphs of mdseg_proj_bwd_tc
+  return 2 * (size_t)n_images * c_max * h * w * 4 + 512 + mdseg_proj_bwd_tc_workspace_bytes(graphs, MDSEG_F32);
 }
 
 extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table* graphs, const int32_t* dataset_ids,
@@ -686,7 +687,11 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
     if (int rc = mdseg_up_ce_bwd(src, dataset_ids, labels, label_dtype, n_images, h, w, H, W, ignore, loss_px, lse_px,
                                  states, grad_out, grad_scale, &dA, &dB, stream))
       return rc;
-    return mdseg_proj_bwd(dyA, dyB, c_max, graphs, dataset_ids, n_images, h, w, dx, dx_dtype, stream);
+    // dense graphs: adjoint on the tensor cores, converted graphs behind the two planes in the workspace
+    float* tail = dyB + (size_t)n_images * c_max * hw;
+    const size_t used = (size_t)((unsigned char*)tail - (unsigned char*)workspace);
+    return mdseg_proj_bwd_tc(dyA, dyB, c_max, graphs, dataset_ids, n_images, h, w, dx, dx_dtype, tail,
+                             workspace_bytes - used, stream);
   }
 
   Args a;

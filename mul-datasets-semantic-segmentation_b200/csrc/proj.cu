@@ -369,7 +369,7 @@ int launch_fwd(const void* x, const mdseg_graph_table* t, const int32_t* ids, in
 
 template <typename T>
 int launch_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* t, const int32_t* ids,
-               int n_images, int64_t hw, void* dx, cudaStream_t s) {
+               int n_images, int64_t hw, void* dx, unsigned skip_mask, cudaStream_t s) {
   constexpr int PXV = 16 / sizeof(T);
   {  // the sparse kernel also zero-fills images with an invalid dataset id
     const bool vec = (hw % PXV == 0) && ((((uintptr_t)dx | (uintptr_t)dyA | (uintptr_t)dyB) & 15) == 0);
@@ -382,9 +382,9 @@ int launch_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph
     else proj_bwd_sparse_kernel<T, 1><<<grid, 256, 0, s>>>(dyA, dyB, y_cmax, *t, ids, hw, (T*)dx);
     MDSEG_LAUNCH_OK();
   }
-  if (any_dense(t)) {
+  if (any_dense(t, skip_mask)) {
     dim3 grid((unsigned)ceil_div64(hw, kTP), (unsigned)((t->C_uni + kTO - 1) / kTO), (unsigned)n_images);
-    proj_dense_kernel<float, T, false><<<grid, 256, 0, s>>>(dyA, dyB, *t, ids, hw, y_cmax, t->C_uni, (T*)dx, 0u);
+    proj_dense_kernel<float, T, false><<<grid, 256, 0, s>>>(dyA, dyB, *t, ids, hw, y_cmax, t->C_uni, (T*)dx, skip_mask);
     MDSEG_LAUNCH_OK();
   }
   return 0;
@@ -433,23 +433,30 @@ extern "C" int mdseg_proj_fwd(const void* x, int dtype, const mdseg_graph_table*
                               (cudaStream_t)stream);
 }
 
-extern "C" int mdseg_proj_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* graphs,
-                              const int32_t* dataset_ids, int n_images, int h, int w, void* dx, int dtype,
-                              void* stream) {
-  using namespace mdseg;
+namespace mdseg {
+// Adjoint of every dataset whose bit is clear in skip_mask (plus the zero fill of images without a dataset).
+int proj_bwd_rest(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* graphs,
+                  const int32_t* dataset_ids, int n_images, int h, int w, void* dx, int dtype, unsigned skip_mask,
+                  cudaStream_t s) {
   if (int rc = check_table(graphs, "mdseg_proj_bwd")) return rc;
   MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0, "mdseg_proj_bwd: bad shape");
   if (n_images == 0) return 0;
   MDSEG_REQUIRE(dyA && dx, "mdseg_proj_bwd: null pointer");
   const int64_t hw = (int64_t)h * w;
-  cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case MDSEG_F32: return launch_bwd<float>(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dx, s);
-    case MDSEG_BF16: return launch_bwd<__nv_bfloat16>(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dx, s);
-    case MDSEG_F16: return launch_bwd<__half>(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dx, s);
+    case MDSEG_F32: return launch_bwd<float>(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dx, skip_mask, s);
+    case MDSEG_BF16: return launch_bwd<__nv_bfloat16>(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dx, skip_mask, s);
+    case MDSEG_F16: return launch_bwd<__half>(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dx, skip_mask, s);
   }
   set_error("mdseg_proj_bwd: unsupported dtype %d", dtype);
   return 2;
+}
+}  // namespace mdseg
+
+extern "C" int mdseg_proj_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* graphs,
+                              const int32_t* dataset_ids, int n_images, int h, int w, void* dx, int dtype,
+                              void* stream) {
+  return mdseg::proj_bwd_rest(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, h, w, dx, dtype, 0u, (cudaStream_t)stream);
 }
 
 extern "C" int mdseg_proj_bwd_graph(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,

@@ -50,6 +50,11 @@ struct TcArgs {
   int n_chunks;
   int a_stage_bytes, b_stage_bytes;      // per stage, all terms
   int fmt;                               // UMMA 16-bit format: 0 = F16, 1 = BF16
+  // adjoint (dx = G^T (dyA + dyB)): K = C_ds, N = a tile of `nt` unified channels (blockIdx.z)
+  const float* dyA;
+  const float* dyB;                      // may be NULL
+  void* dx;
+  int nt;                                // unified channels per N tile, multiple of 16
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,12 +200,51 @@ __global__ void __launch_bounds__(256) proj_tc_prep_kernel(const mdseg_graph_tab
   }
 }
 
+// adjoint: B[row = u - u0][k = n] = G_d[n][u]; dataset d holds n_tiles x n_chunks(d) chunks of TERMS x [nt][32 k]
+template <int TERMS>
+__global__ void __launch_bounds__(256) proj_tc_prep_bwd_kernel(const mdseg_graph_table tab, int n_tiles, int fmt,
+                                                               unsigned char* gw, const TcArgs a) {
+  const int d = blockIdx.y;
+  if (!((a.tc_mask >> d) & 1u)) return;
+  const mdseg_sparse_graph g = tab.g[d];
+  const int nt = a.nt;
+  const int n_chunks = (g.C_ds + kKB - 1) / kKB;
+  const int groups = n_tiles * n_chunks * 4 * nt;  // (tile, chunk, k-group of 8, row)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += gridDim.x * blockDim.x) {
+    const int r = i % nt, kg = (i / nt) % 4, kc = (i / (4 * nt)) % n_chunks, z = i / (4 * nt * n_chunks);
+    const int u = z * nt + r;
+    uint32_t w[TERMS][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = kc * kKB + kg * 8 + 2 * j;
+      float v0 = 0.f, v1 = 0.f;
+      if (u < tab.C_uni) {
+        if (n < g.C_ds) v0 = g.dense[(int64_t)n * tab.C_uni + u];
+        if (n + 1 < g.C_ds) v1 = g.dense[(int64_t)(n + 1) * tab.C_uni + u];
+      }
+      uint32_t o[TERMS];
+      Split<TERMS>::pair(v0, v1, fmt, o);
+#pragma unroll
+      for (int t = 0; t < TERMS; ++t) w[t][j] = o[t];
+    }
+    unsigned char* chunk = gw + a.g_off[d] + ((int64_t)z * n_chunks + kc) * TERMS * nt * 64;
+#pragma unroll
+    for (int t = 0; t < TERMS; ++t)
+      *reinterpret_cast<uint4*>(chunk + (int64_t)t * nt * 64 + kg * (nt * 16) + r * 16) =
+          make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+  }
+}
+
 // ---- main kernel -------------------------------------------------------------------------------------------
-template <typename T, int TERMS>
-__global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_constant__ TcArgs a) {
+// kBwd = false: y[n][p] = sum_c G[n][c] x[c][p]       (T = dtype of x, output fp32)
+// kBwd = true : dx[u][p] = sum_n G[n][u] dy[n][p]      (T = dtype of dx, input fp32 planes dyA (+ dyB))
+template <typename T, int TERMS, bool kBwd>
+__global__ void __launch_bounds__(kTcThreads, kBwd ? 4 : 2) proj_tc_kernel(const __grid_constant__ TcArgs a) {
+  // the adjoint has one to eight K chunks per CTA: one stage and four CTAs per SM overlap better than two stages
+  constexpr int kNS = kBwd ? 1 : kStagesTc;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_b[kStagesTc];    // B chunk landed (bulk copy complete_tx)
-  __shared__ __align__(8) uint64_t bar_mma[kStagesTc];  // the MMAs that read the stage have retired
+  __shared__ __align__(8) uint64_t bar_b[kNS];    // B chunk landed (bulk copy complete_tx)
+  __shared__ __align__(8) uint64_t bar_mma[kNS];  // the MMAs that read the stage have retired
   __shared__ __align__(8) uint64_t bar_acc;             // accumulator complete
   __shared__ uint32_t tmem_base_s;
 
@@ -208,19 +252,23 @@ __global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_consta
   const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
   if (d < 0 || d >= a.n_datasets || !((a.tc_mask >> d) & 1u)) return;  // uniform per CTA
   const int C_ds = a.C_ds[d];
-  const int npad = pad16(C_ds);
+  const int u0 = kBwd ? (int)blockIdx.z * a.nt : 0;                      // first output channel of this N tile
+  const int n_out = kBwd ? ((a.C_uni - u0) < a.nt ? (a.C_uni - u0) : a.nt) : C_ds;  // valid output channels
+  const int npad = kBwd ? a.nt : pad16(C_ds);
+  const int K = kBwd ? C_ds : a.C_uni;
+  const int n_chunks = (K + kKB - 1) / kKB;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (kTM - 1), khalf = tid >> 7;  // pixel of the tile, half of the K-chunk
   const long long p = (long long)blockIdx.x * kTM + row;
   const bool p_ok = p < a.hw;
 
   unsigned char* sA = smem;                                        // [stage][term][4 k-groups][128 rows][16 B]
-  unsigned char* sB = smem + (size_t)kStagesTc * a.a_stage_bytes;   // [stage][term][4 k-groups][npad rows][16 B]
+  unsigned char* sB = smem + (size_t)kNS * a.a_stage_bytes;   // [stage][term][4 k-groups][npad rows][16 B]
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < npad) tmem_cols <<= 1;
 
   if (tid == 0) {
-    for (int s = 0; s < kStagesTc; ++s) { bar_init(&bar_b[s], 1); bar_init(&bar_mma[s], 1); }
+    for (int s = 0; s < kNS; ++s) { bar_init(&bar_b[s], 1); bar_init(&bar_mma[s], 1); }
     bar_init(&bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -233,9 +281,11 @@ __global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  const T* xb = (const T*)a.x + (long long)b * a.C_uni * a.hw;
-  const unsigned char* gchunks = a.gw + a.g_off[d];
+  const T* xb = kBwd ? nullptr : (const T*)a.x + (long long)b * a.C_uni * a.hw;
+  const float* dA = kBwd ? a.dyA + (long long)b * a.y_cmax * a.hw : nullptr;
+  const float* dB = (kBwd && a.dyB) ? a.dyB + (long long)b * a.y_cmax * a.hw : nullptr;
   const uint32_t b_chunk_bytes = (uint32_t)(TERMS * npad * 64);
+  const unsigned char* gchunks = a.gw + a.g_off[d] + (kBwd ? (size_t)blockIdx.z * n_chunks * b_chunk_bytes : 0);
   const uint32_t idesc = umma_idesc(a.fmt, npad);
 
   // this thread's 16 channels of a chunk, one chunk ahead in registers so that the HBM latency of chunk kc + 1
@@ -245,20 +295,29 @@ __global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_consta
 #pragma unroll
     for (int j = 0; j < kKB / 2; ++j) {
       const int c = kc * kKB + khalf * (kKB / 2) + j;
-      vn[j] = (p_ok && c < a.C_uni) ? to_f32<T>(xb[(long long)c * a.hw + p]) : 0.f;
+      float v = 0.f;
+      if (p_ok && c < K) {
+        if constexpr (kBwd) {
+          v = dA[(long long)c * a.hw + p];
+          if (dB) v += dB[(long long)c * a.hw + p];
+        } else {
+          v = to_f32<T>(xb[(long long)c * a.hw + p]);
+        }
+      }
+      vn[j] = v;
     }
   };
   load_chunk(0);
 
-  for (int kc = 0; kc < a.n_chunks; ++kc) {
-    const int s = kc % kStagesTc;
-    const uint32_t use = (uint32_t)(kc / kStagesTc);
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int s = kc % kNS;
+    const uint32_t use = (uint32_t)(kc / kNS);
     float v[kKB / 2];
 #pragma unroll
     for (int j = 0; j < kKB / 2; ++j) v[j] = vn[j];
-    if (kc + 1 < a.n_chunks) load_chunk(kc + 1);
+    if (kc + 1 < n_chunks) load_chunk(kc + 1);
     // the MMAs of chunk kc - kStages have finished reading stage s
-    if (kc >= kStagesTc) bar_wait(&bar_mma[s], (use - 1) & 1u);
+    if (kc >= kNS) bar_wait(&bar_mma[s], (use - 1) & 1u);
     unsigned char* stA = sA + (size_t)s * a.a_stage_bytes;
     unsigned char* stB = sB + (size_t)s * a.b_stage_bytes;
     if (tid == 0) {
@@ -303,7 +362,7 @@ __global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_consta
         }
       }
       tc_commit(&bar_mma[s]);                       // frees the stage when these MMAs retire
-      if (kc == a.n_chunks - 1) tc_commit(&bar_acc);  // ... and the accumulator is complete
+      if (kc == n_chunks - 1) tc_commit(&bar_acc);  // ... and the accumulator is complete
     }
   }
 
@@ -311,13 +370,18 @@ __global__ void __launch_bounds__(kTcThreads) proj_tc_kernel(const __grid_consta
   // quarter take alternate groups of 16 columns
   bar_wait(&bar_acc, 0);
   tc_fence_after();
-  float* yb = a.y + (long long)b * a.y_cmax * a.hw;
+  float* yb = kBwd ? nullptr : a.y + (long long)b * a.y_cmax * a.hw;
+  T* dxb = kBwd ? (T*)a.dx + ((long long)b * a.C_uni + u0) * a.hw : nullptr;
   for (int n0 = (warp >> 2) * 16; n0 < npad; n0 += 32) {
     float acc[16];
     tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)n0, acc);
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (p_ok && n0 + i < C_ds) yb[(long long)(n0 + i) * a.hw + p] = acc[i];
+    for (int i = 0; i < 16; ++i) {
+      if (p_ok && n0 + i < n_out) {
+        if constexpr (kBwd) dxb[(long long)(n0 + i) * a.hw + p] = from_f32<T>(acc[i]);
+        else yb[(long long)(n0 + i) * a.hw + p] = acc[i];
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -364,6 +428,7 @@ extern "C" int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_tab
   a.hw = (long long)h * w;
   a.n_chunks = (graphs->C_uni + kKB - 1) / kKB;
   a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  a.dyA = nullptr; a.dyB = nullptr; a.dx = nullptr; a.nt = 0;
   const int terms = terms_of(dtype);
   a.tc_mask = 0;
   int npad_max = 0;
@@ -394,7 +459,7 @@ extern "C" int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_tab
     proj_tc_prep_kernel<TERMS><<<pgrid, 256, 0, s>>>(*graphs, a.tc_mask, a.n_chunks, a.fmt,                        \
                                                      const_cast<unsigned char*>(a.gw), a);                         \
     MDSEG_LAUNCH_OK();                                                                                             \
-    auto k = proj_tc_kernel<T, TERMS>;                                                                             \
+    auto k = proj_tc_kernel<T, TERMS, false>;                                                                      \
     MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
     k<<<grid, kTcThreads, smem, s>>>(a);                                                                                  \
     MDSEG_LAUNCH_OK();                                                                                             \
@@ -405,5 +470,98 @@ extern "C" int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_tab
     case MDSEG_F16: MDSEG_TC_LAUNCH(__half, 1); break;
   }
 #undef MDSEG_TC_LAUNCH
+  return 0;
+}
+
+// ---- adjoint on the tensor cores ---------------------------------------------------------------------------
+namespace mdseg {
+int proj_bwd_rest(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* graphs,
+                  const int32_t* dataset_ids, int n_images, int h, int w, void* dx, int dtype, unsigned skip_mask,
+                  cudaStream_t s);
+namespace {
+// N tiling of the unified channels: tiles of at most 128 (four CTAs of 48 KB and 128 TMEM columns per SM)
+void bwd_tiling(int C_uni, int* n_tiles, int* nt) {
+  *n_tiles = (C_uni + 127) / 128;
+  *nt = pad16((C_uni + *n_tiles - 1) / *n_tiles);
+}
+}  // namespace
+}  // namespace mdseg
+
+extern "C" size_t mdseg_proj_bwd_tc_workspace_bytes(const mdseg_graph_table* graphs, int dtype) {
+  using namespace mdseg;
+  if (!graphs || graphs->n_datasets <= 0 || graphs->n_datasets > MDSEG_MAX_DATASETS || graphs->C_uni <= 0) return 256;
+  int n_tiles, nt;
+  bwd_tiling(graphs->C_uni, &n_tiles, &nt);
+  size_t total = 256;
+  for (int i = 0; i < graphs->n_datasets; ++i)
+    if (tc_dataset(graphs->g[i], graphs->C_uni))
+      total += (size_t)n_tiles * ((graphs->g[i].C_ds + kKB - 1) / kKB) * terms_of(dtype) * nt * 64;
+  return total;
+}
+
+extern "C" int mdseg_proj_bwd_tc(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* graphs,
+                                 const int32_t* dataset_ids, int n_images, int h, int w, void* dx, int dtype,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(graphs && graphs->n_datasets > 0 && graphs->n_datasets <= MDSEG_MAX_DATASETS && graphs->C_uni > 0,
+                "mdseg_proj_bwd_tc: bad graph table");
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0, "mdseg_proj_bwd_tc: bad shape");
+  MDSEG_REQUIRE(is_float_dtype(dtype), "mdseg_proj_bwd_tc: unsupported dtype %d", dtype);
+  if (n_images == 0) return 0;
+  MDSEG_REQUIRE(dyA && dx && workspace, "mdseg_proj_bwd_tc: null pointer");
+  MDSEG_REQUIRE(workspace_bytes >= mdseg_proj_bwd_tc_workspace_bytes(graphs, dtype),
+                "mdseg_proj_bwd_tc: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+
+  TcArgs a;
+  a.x = nullptr; a.y = nullptr; a.dataset_ids = dataset_ids;
+  a.gw = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  a.n_datasets = graphs->n_datasets; a.C_uni = graphs->C_uni; a.y_cmax = y_cmax;
+  a.hw = (long long)h * w;
+  a.n_chunks = 0;
+  a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  a.dyA = dyA; a.dyB = dyB; a.dx = dx;
+  int n_tiles;
+  bwd_tiling(graphs->C_uni, &n_tiles, &a.nt);
+  const int terms = terms_of(dtype);
+  a.tc_mask = 0;
+  long long off = 0;
+  int max_groups = 0;
+  for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
+    a.g_off[i] = 0; a.C_ds[i] = 0;
+    if (i >= graphs->n_datasets) continue;
+    a.C_ds[i] = graphs->g[i].C_ds;
+    if (!tc_dataset(graphs->g[i], graphs->C_uni)) continue;
+    MDSEG_REQUIRE(y_cmax >= graphs->g[i].C_ds, "mdseg_proj_bwd_tc: y_cmax %d < C_ds %d", y_cmax, graphs->g[i].C_ds);
+    a.tc_mask |= 1u << i;
+    a.g_off[i] = off;
+    const int nch = (graphs->g[i].C_ds + kKB - 1) / kKB;
+    off += (long long)n_tiles * nch * terms * a.nt * 64;
+    max_groups = n_tiles * nch * 4 * a.nt > max_groups ? n_tiles * nch * 4 * a.nt : max_groups;
+  }
+  // sparse graphs, dense ones outside the envelope and the zero fill of images without a dataset: proj.cu
+  if (int rc = proj_bwd_rest(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, h, w, dx, dtype, a.tc_mask, s)) return rc;
+  if (!a.tc_mask) return 0;
+
+  a.a_stage_bytes = terms * 4 * kTM * 16;
+  a.b_stage_bytes = terms * a.nt * 64;
+  const size_t smem = (size_t)(a.a_stage_bytes + a.b_stage_bytes);  // one stage (kNS == 1 in the adjoint)
+  const dim3 pgrid((unsigned)((max_groups + 255) / 256), (unsigned)graphs->n_datasets);
+  const dim3 grid((unsigned)((a.hw + kTM - 1) / kTM), (unsigned)n_images, (unsigned)n_tiles);
+#define MDSEG_TCB_LAUNCH(T, TERMS)                                                                                 \
+  do {                                                                                                             \
+    proj_tc_prep_bwd_kernel<TERMS><<<pgrid, 256, 0, s>>>(*graphs, n_tiles, a.fmt, const_cast<unsigned char*>(a.gw), a); \
+    MDSEG_LAUNCH_OK();                                                                                             \
+    auto k = proj_tc_kernel<T, TERMS, true>;                                                                       \
+    MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    k<<<grid, kTcThreads, smem, s>>>(a);                                                                           \
+    MDSEG_LAUNCH_OK();                                                                                             \
+  } while (0)
+  switch (dtype) {
+    case MDSEG_F32: MDSEG_TCB_LAUNCH(float, 3); break;
+    case MDSEG_BF16: MDSEG_TCB_LAUNCH(__nv_bfloat16, 1); break;
+    case MDSEG_F16: MDSEG_TCB_LAUNCH(__half, 1); break;
+  }
+#undef MDSEG_TCB_LAUNCH
   return 0;
 }

@@ -601,8 +601,14 @@ class _MdsProjOhemCE(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            N.call("mdseg_proj_bwd", _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dx),
-                   _DT[x.dtype], _stream())
+            if any(tab.g[i].dense for i in range(tab.n_datasets)):  # dense graphs: adjoint on the tensor cores
+                nb = N.lib.mdseg_proj_bwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
+                ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+                N.call("mdseg_proj_bwd_tc", _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dx),
+                       _DT[x.dtype], _ptr(ws), nb, _stream())
+            else:
+                N.call("mdseg_proj_bwd", _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dx),
+                       _DT[x.dtype], _stream())
         dgs = [None] * n
         if want_dg:
             stride = cmax * Cu

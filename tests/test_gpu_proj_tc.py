@@ -89,3 +89,39 @@ def test_proj_tc_loss_and_gradients_match_reference_ops(ops):
     assert rel_err(xd.grad.cpu().numpy(), want["dlogits_uni"]) <= 1e-5
     for i in range(len(n_cats)):
         assert rel_err(gd[i].grad.cpu().numpy(), want["dgraphs"][i]) <= 2e-5
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("two_planes", [False, True])
+def test_proj_bwd_tc_matches_float64_einsum(ops, case, dt, two_planes):
+    """mdseg_proj_bwd_tc: dx[b, u] = sum_n G_d[n, u] (dyA + dyB)[b, n] — dense graphs on the tensor cores, sparse
+    ones and an image without a dataset (zero gradient) through the proj.cu kernels of the same call."""
+    import ctypes as C
+    from mdseg_b200 import native as N
+    n_cats, kinds, c_uni, ids, h, w = CASES[case]
+    ids = list(ids) + [-1]  # last image: not part of the loss
+    B, cmax = len(ids), max(n_cats)
+    g = torch.Generator().manual_seed(300 + case)
+    graphs = [dense_graph(g, c, c_uni) if k == "d" else onehot_graph(g, c, c_uni) for c, k in zip(n_cats, kinds)]
+    dev_graphs = [m.to(DEV).requires_grad_(k == "d") for m, k in zip(graphs, kinds)]
+    dyA = torch.randn(B, cmax, h, w, generator=g)
+    dyB = torch.randn(B, cmax, h, w, generator=g) if two_planes else None
+    tab, keep = ops._default_graphs.table(dev_graphs)
+    dx = torch.full((B, c_uni, h, w), 7.0, dtype=dt, device=DEV)
+    ids_t = torch.tensor(ids, dtype=torch.int32, device=DEV)
+    a, b = dyA.to(DEV), (dyB.to(DEV) if two_planes else None)
+    nb = N.lib.mdseg_proj_bwd_tc_workspace_bytes(C.byref(tab), ops._DT[dt])
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    N.call("mdseg_proj_bwd_tc", a.data_ptr(), b.data_ptr() if two_planes else None, cmax, C.byref(tab),
+           ids_t.data_ptr(), B, h, w, dx.data_ptr(), ops._DT[dt], ws.data_ptr(), nb, ops._stream())
+    torch.cuda.synchronize()
+    tol = 1e-5 if dt == torch.float32 else 2e-2
+    for i, d in enumerate(ids):
+        got = dx[i].float().cpu().numpy()
+        if d < 0:
+            assert not got.any()
+            continue
+        dy = dyA[i, :n_cats[d]].double() + (dyB[i, :n_cats[d]].double() if two_planes else 0)
+        want = torch.einsum("nhw,nc->chw", dy, graphs[d].double()).numpy()
+        assert rel_err(got, want) <= tol, (i, d, rel_err(got, want))
