@@ -300,6 +300,18 @@ int mdseg_proj_bwd_graph(const void* x, int dtype, const float* dyA,
                          const int32_t* dataset_ids, int n_images, int h, int w,
                          float* dG, long long dg_stride, void* stream);
 
+/* The same with the dense graphs on the tcgen05 tensor cores: K = the pixels of an image slab
+ * (both operands are K-major in HBM), one 128-class M tile and all of C_uni (<= 512) per CTA,
+ * per-CTA partial sums in `workspace`, then a fixed-order reduction into dG (deterministic;
+ * the FFMA route uses atomics).  Precision as mdseg_proj_fwd_tc. */
+size_t mdseg_proj_bwd_graph_tc_workspace_bytes(const mdseg_graph_table* graphs /*host*/,
+                                               int n_images, int h, int w);
+int mdseg_proj_bwd_graph_tc(const void* x, int dtype, const float* dyA, const float* dyB,
+                            int y_cmax, const mdseg_graph_table* graphs /*host*/,
+                            const int32_t* dataset_ids, int n_images, int h, int w,
+                            float* dG, long long dg_stride, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* ---- a6 + a7 (+ a10): fused bilinear upsample (align_corners=True) + CE -------
  * For every label pixel (Y,X) of image b: interpolate the C low-res logits of
  * the image's source (see mdseg_src_table) to (Y,X) exactly as

@@ -263,11 +263,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 proj_dgraph_kernel(const T* __restrict__ x, const float* __restrict__ dyA, const float* __restrict__ dyB, int y_cmax,
                    const mdseg_graph_table tab, const int32_t* __restrict__ dataset_ids, int64_t hw, int64_t slab,
-                   float* __restrict__ dG, long long dg_stride) {
+                   float* __restrict__ dG, long long dg_stride, unsigned skip_mask) {
   const int n_slabs = (int)((hw + slab - 1) / slab);
   const int b = blockIdx.z / n_slabs, sl = blockIdx.z % n_slabs;
   const int d = dataset_ids ? dataset_ids[b] : 0;
-  if (d < 0 || d >= tab.n_datasets) return;
+  if (d < 0 || d >= tab.n_datasets || ((skip_mask >> d) & 1u)) return;
   const mdseg_sparse_graph g = tab.g[d];
   const int n0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   if (n0 >= g.C_ds || c0 >= tab.C_uni) return;
@@ -392,12 +392,14 @@ int launch_bwd(const float* dyA, const float* dyB, int y_cmax, const mdseg_graph
 
 template <typename T>
 int launch_dgraph(const void* x, const float* dyA, const float* dyB, int y_cmax, const mdseg_graph_table* t,
-                  const int32_t* ids, int n_images, int64_t hw, float* dG, long long dg_stride, cudaStream_t s) {
+                  const int32_t* ids, int n_images, int64_t hw, float* dG, long long dg_stride, unsigned skip_mask,
+                  cudaStream_t s) {
   // pixel slabs: enough CTAs to fill the chip, at least 2048 px each
   int64_t slab = 2048;
   const int n_slabs = (int)ceil_div64(hw, slab);
   dim3 grid((unsigned)((t->C_uni + 31) / 32), (unsigned)((max_cds(t) + 31) / 32), (unsigned)(n_images * n_slabs));
-  proj_dgraph_kernel<T><<<grid, 256, 0, s>>>((const T*)x, dyA, dyB, y_cmax, *t, ids, hw, slab, dG, dg_stride);
+  proj_dgraph_kernel<T><<<grid, 256, 0, s>>>((const T*)x, dyA, dyB, y_cmax, *t, ids, hw, slab, dG, dg_stride,
+                                             skip_mask);
   MDSEG_LAUNCH_OK();
   return 0;
 }
@@ -459,22 +461,33 @@ extern "C" int mdseg_proj_bwd(const float* dyA, const float* dyB, int y_cmax, co
   return mdseg::proj_bwd_rest(dyA, dyB, y_cmax, graphs, dataset_ids, n_images, h, w, dx, dtype, 0u, (cudaStream_t)stream);
 }
 
-extern "C" int mdseg_proj_bwd_graph(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,
-                                    const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images, int h,
-                                    int w, float* dG, long long dg_stride, void* stream) {
-  using namespace mdseg;
+namespace mdseg {
+// d bi_graph of every dataset whose bit is clear in skip_mask (atomic accumulation into dG).
+int proj_dgraph_rest(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,
+                     const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images, int h, int w, float* dG,
+                     long long dg_stride, unsigned skip_mask, cudaStream_t s) {
   if (int rc = check_table(graphs, "mdseg_proj_bwd_graph")) return rc;
   MDSEG_REQUIRE(n_images >= 0 && h > 0 && w > 0, "mdseg_proj_bwd_graph: bad shape");
   if (n_images == 0) return 0;
   MDSEG_REQUIRE(x && dyA && dG, "mdseg_proj_bwd_graph: null pointer");
   const int64_t hw = (int64_t)h * w;
   MDSEG_REQUIRE((int64_t)n_images * ceil_div64(hw, 2048) <= 65535, "mdseg_proj_bwd_graph: grid too large");
-  cudaStream_t s = (cudaStream_t)stream;
+  bool any = false;
+  for (int i = 0; i < graphs->n_datasets; ++i) any = any || !((skip_mask >> i) & 1u);
+  if (!any) return 0;
   switch (dtype) {
-    case MDSEG_F32: return launch_dgraph<float>(x, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dG, dg_stride, s);
-    case MDSEG_BF16: return launch_dgraph<__nv_bfloat16>(x, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dG, dg_stride, s);
-    case MDSEG_F16: return launch_dgraph<__half>(x, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dG, dg_stride, s);
+    case MDSEG_F32: return launch_dgraph<float>(x, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dG, dg_stride, skip_mask, s);
+    case MDSEG_BF16: return launch_dgraph<__nv_bfloat16>(x, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dG, dg_stride, skip_mask, s);
+    case MDSEG_F16: return launch_dgraph<__half>(x, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, hw, dG, dg_stride, skip_mask, s);
   }
   set_error("mdseg_proj_bwd_graph: unsupported dtype %d", dtype);
   return 2;
+}
+}  // namespace mdseg
+
+extern "C" int mdseg_proj_bwd_graph(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,
+                                    const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images, int h,
+                                    int w, float* dG, long long dg_stride, void* stream) {
+  return mdseg::proj_dgraph_rest(x, dtype, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, h, w, dG, dg_stride, 0u,
+                                 (cudaStream_t)stream);
 }

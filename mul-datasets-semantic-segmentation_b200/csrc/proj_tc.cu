@@ -565,3 +565,330 @@ extern "C" int mdseg_proj_bwd_tc(const float* dyA, const float* dyB, int y_cmax,
 #undef MDSEG_TCB_LAUNCH
   return 0;
 }
+
+// ---- d bi_graph on the tensor cores ------------------------------------------------------------------------
+//   dG_d[n][c] += sum over the images b of dataset d and the pixels p of  (dyA + dyB)[b][n][p] * x[b][c][p]
+// GEMM per CTA: D[M = 128 classes (one of at most two M tiles), N = C_uni padded to 16 (<= 384, issued as N tiles
+// of <= 256; 512 TMEM columns allocated)] over K = one slab of the image's pixels.  Both operands are K-major in HBM already (pixels
+// are contiguous), so a thread copies 8 consecutive pixels of one row (32 bytes of fp32), converts them to the 16-bit
+// terms and writes one 16-byte K-group per term.  Every element of dy and x is read and converted once per M tile.
+// The CTA's 128 x Npad accumulator goes to a slot of the workspace; proj_tc_dgraph_reduce_kernel adds the slots of
+// a dataset in a fixed order (deterministic, no atomics).
+namespace mdseg {
+int proj_dgraph_rest(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,
+                     const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images, int h, int w, float* dG,
+                     long long dg_stride, unsigned skip_mask, cudaStream_t s);
+namespace {
+
+constexpr int kDgM = 128;        // classes per M tile
+constexpr int kDgMaxN = 384;     // unified channels (padded): (128 + 384) rows x 4 K-groups = 8 items per thread
+constexpr int kDgItems = 8;      // (row, K-group) items per thread and chunk
+
+struct DgArgs {
+  const void* x;
+  const float* dyA;
+  const float* dyB;
+  const int32_t* dataset_ids;
+  float* part;                 // [n_images][2 M tiles][n_slabs][128][npad]
+  int C_ds[MDSEG_MAX_DATASETS];
+  unsigned tc_mask;
+  int n_datasets, C_uni, npad, y_cmax;
+  long long hw, slab;
+  int n_slabs, fmt;
+  int a_stage_bytes, b_stage_bytes;
+};
+
+template <typename T, int TERMS>
+__global__ void __launch_bounds__(kTcThreads, 1) proj_tc_dgraph_kernel(const __grid_constant__ DgArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_mma[kStagesTc];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_s;
+
+  const int b = blockIdx.z, mt = blockIdx.y, sl = blockIdx.x;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  if (d < 0 || d >= a.n_datasets || !((a.tc_mask >> d) & 1u)) return;
+  const int C_ds = a.C_ds[d];
+  const int n0 = mt * kDgM;
+  if (n0 >= C_ds) return;
+  const int npad = a.npad;
+  const int R = kDgM + npad;  // rows staged per chunk: 128 of dy, npad of x
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const long long p_beg = (long long)sl * a.slab;
+  const long long p_end = (p_beg + a.slab < a.hw) ? p_beg + a.slab : a.hw;
+  const int n_chunks = (int)((p_end - p_beg + kKB - 1) / kKB);
+
+  unsigned char* sA = smem;                                       // [stage][term][4 k-groups][128 rows][16 B]
+  unsigned char* sB = smem + (size_t)kStagesTc * a.a_stage_bytes;  // [stage][term][4 k-groups][npad rows][16 B]
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < npad) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesTc; ++s) bar_init(&bar_mma[s], 1);
+    bar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  const T* xb = (const T*)a.x + (long long)b * a.C_uni * a.hw;
+  const float* dA = a.dyA + (long long)b * a.y_cmax * a.hw;
+  const float* dB = a.dyB ? a.dyB + (long long)b * a.y_cmax * a.hw : nullptr;
+  const bool vec_ok = (a.hw % 8 == 0) && (p_beg % 8 == 0);  // 8 consecutive pixels are 32-byte aligned in every row
+
+  // This thread's (row, K-group) items — the same for every chunk: consecutive threads take consecutive rows of one
+  // K-group (conflict-free 16-byte shared-memory stores; a 32-byte sector of HBM per thread and load).
+  const int n_items = R * 4;  // <= kDgItems * kTcThreads (npad <= 384)
+  const float* srcA[kDgItems];  // dy rows: plane A (and B at the same offset)
+  const T* srcX[kDgItems];      // x rows
+  int dst_off[kDgItems], kind[kDgItems];  // kind: 0 = none / zero row, 1 = dy row, 2 = x row
+#pragma unroll
+  for (int j = 0; j < kDgItems; ++j) {
+    const int it = j * kTcThreads + tid;
+    srcA[j] = nullptr; srcX[j] = nullptr; dst_off[j] = -1; kind[j] = 0;
+    if (it < n_items) {
+      const int r = it % R, kg = it / R;
+      if (r < kDgM) {
+        dst_off[j] = kg * (kDgM * 16) + r * 16;
+        if (n0 + r < C_ds) { kind[j] = 1; srcA[j] = dA + (long long)(n0 + r) * a.hw + p_beg + kg * 8; }
+      } else {
+        dst_off[j] = a.a_stage_bytes * kStagesTc + kg * (npad * 16) + (r - kDgM) * 16;  // relative to sA of stage 0 ...
+        if (r - kDgM < a.C_uni) { kind[j] = 2; srcX[j] = xb + (long long)(r - kDgM) * a.hw + p_beg + kg * 8; }
+      }
+    }
+  }
+  const long long plane_b_off = dB ? (dB - dA) : 0;
+
+  // 8 consecutive pixels of item j in chunk kc (zero beyond the matrices / the slab)
+  auto load8 = [&](int j, int kc, float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    const long long off = (long long)kc * kKB;
+    const long long p = p_beg + off + ((j * kTcThreads + tid) / R) * 8;
+    if (kind[j] == 1) {
+      const float* q = srcA[j] + off;
+      if (vec_ok && p + 8 <= p_end) {
+        const float4 u0 = *reinterpret_cast<const float4*>(q), u1 = *reinterpret_cast<const float4*>(q + 4);
+        v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        if (dB) {
+          const float* q2 = q + plane_b_off;
+          const float4 w0 = *reinterpret_cast<const float4*>(q2), w1 = *reinterpret_cast<const float4*>(q2 + 4);
+          v[0] += w0.x; v[1] += w0.y; v[2] += w0.z; v[3] += w0.w; v[4] += w1.x; v[5] += w1.y; v[6] += w1.z; v[7] += w1.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (p + i < p_end) v[i] = q[i] + (dB ? q[plane_b_off + i] : 0.f);
+      }
+    } else if (kind[j] == 2) {
+      const T* q = srcX[j] + off;
+      if (vec_ok && p + 8 <= p_end) {
+        if constexpr (sizeof(T) == 4) {
+          const float4 u0 = *reinterpret_cast<const float4*>(q), u1 = *reinterpret_cast<const float4*>(q + 4);
+          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        } else {
+          VecLoad<T, 8>::load(q, v);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (p + i < p_end) v[i] = to_f32<T>(q[i]);
+      }
+    }
+  };
+
+  const int n_tiles_n = (npad + kMaxN - 1) / kMaxN;
+  const int nt_n = pad16((npad + n_tiles_n - 1) / n_tiles_n);  // N tile width of one UMMA (<= 256)
+
+  // one chunk ahead in registers: the HBM latency of chunk kc + 1 hides behind the conversion of chunk kc
+  float vn[kDgItems][8];
+#pragma unroll
+  for (int j = 0; j < kDgItems; ++j) load8(j, 0, vn[j]);
+
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int s = kc % kStagesTc;
+    const uint32_t use = (uint32_t)(kc / kStagesTc);
+    float v[kDgItems][8];
+#pragma unroll
+    for (int j = 0; j < kDgItems; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] = vn[j][i];
+    if (kc + 1 < n_chunks) {
+#pragma unroll
+      for (int j = 0; j < kDgItems; ++j) load8(j, kc + 1, vn[j]);
+    }
+    if (kc >= kStagesTc) bar_wait(&bar_mma[s], (use - 1) & 1u);
+    unsigned char* stA = sA + (size_t)s * a.a_stage_bytes;
+    unsigned char* stB = sB + (size_t)s * a.b_stage_bytes;
+#pragma unroll
+    for (int j = 0; j < kDgItems; ++j) {
+      if (dst_off[j] >= 0) {
+        uint32_t w[TERMS][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o[TERMS];
+          Split<TERMS>::pair(v[j][2 * q], v[j][2 * q + 1], a.fmt, o);
+#pragma unroll
+          for (int t = 0; t < TERMS; ++t) w[t][q] = o[t];
+        }
+        const bool is_a = dst_off[j] < a.a_stage_bytes * kStagesTc;
+        unsigned char* dst = is_a ? stA + dst_off[j] : stB + (dst_off[j] - a.a_stage_bytes * kStagesTc);
+        const int tstride = is_a ? 4 * kDgM * 16 : 4 * npad * 16;
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t)
+          *reinterpret_cast<uint4*>(dst + t * tstride) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aA = smem_addr(stA), aB = smem_addr(stB);
+      for (int jn = 0; jn < n_tiles_n; ++jn) {
+        const int col0 = jn * nt_n;
+        const int nn = (npad - col0) < nt_n ? (npad - col0) : nt_n;
+        const uint32_t idesc = umma_idesc(a.fmt, nn);
+#pragma unroll
+        for (int ks = 0; ks < kKB / 16; ++ks) {
+          constexpr int kPairs = TERMS == 3 ? 6 : 1;
+          const int ta[6] = {0, 0, 1, 1, 0, 2};
+          const int tb[6] = {0, 1, 0, 1, 2, 0};
+#pragma unroll
+          for (int q = 0; q < kPairs; ++q) {
+            const uint64_t ad = umma_desc(aA + ta[q] * (4 * kDgM * 16) + ks * 2 * (kDgM * 16), kDgM * 16, 128);
+            const uint64_t bd = umma_desc(aB + tb[q] * (4 * npad * 16) + ks * 2 * (npad * 16) + col0 * 16, npad * 16, 128);
+            umma_f16(tmem_d + (uint32_t)col0, ad, bd, idesc, (kc > 0 || ks > 0 || q > 0) ? 1u : 0u);
+          }
+        }
+      }
+      tc_commit(&bar_mma[s]);
+      if (kc == n_chunks - 1) tc_commit(&bar_acc);
+    }
+  }
+
+  // epilogue: TMEM lane = class row of the M tile, columns = unified channels -> this CTA's slot of the workspace
+  bar_wait(&bar_acc, 0);
+  tc_fence_after();
+  float* slot = a.part + (((long long)b * 2 + mt) * a.n_slabs + sl) * (long long)kDgM * npad;
+  const int row = (warp & 3) * 32 + (tid & 31);
+  for (int c0 = (warp >> 2) * 16; c0 < npad; c0 += 32) {
+    float acc[16];
+    tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, acc);
+    float4* o = reinterpret_cast<float4*>(slot + (long long)row * npad + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// dG[d][n][c] += sum of the slots of dataset d in (image, slab) order
+__global__ void __launch_bounds__(256) proj_tc_dgraph_reduce_kernel(const DgArgs a, int n_images, float* __restrict__ dG,
+                                                                    long long dg_stride) {
+  const int d = blockIdx.y;
+  if (!((a.tc_mask >> d) & 1u)) return;
+  const int C_ds = a.C_ds[d];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C_ds * a.C_uni) return;
+  const int n = idx / a.C_uni, c = idx - n * a.C_uni;
+  const int mt = n / kDgM, r = n - mt * kDgM;
+  float sum = 0.f;
+  for (int b = 0; b < n_images; ++b) {
+    if ((a.dataset_ids ? a.dataset_ids[b] : 0) != d) continue;
+    const float* base = a.part + (((long long)b * 2 + mt) * a.n_slabs) * (long long)kDgM * a.npad + (long long)r * a.npad + c;
+    for (int sl = 0; sl < a.n_slabs; ++sl) sum += base[(long long)sl * kDgM * a.npad];
+  }
+  dG[(long long)d * dg_stride + idx] += sum;
+}
+
+bool dg_dataset(const mdseg_sparse_graph& g, int C_uni) { return tc_dataset(g, C_uni) && pad16(C_uni) <= kDgMaxN; }
+
+int dg_slabs(int n_images, long long hw) {
+  long long n = (2LL * sm_count() + n_images - 1) / n_images;  // about two CTAs' worth of work per SM
+  const long long max_slabs = (hw + 1023) / 1024;              // at least 1024 pixels (32 chunks) per CTA
+  if (n > max_slabs) n = max_slabs;
+  if (n < 1) n = 1;
+  return (int)n;
+}
+
+}  // namespace
+}  // namespace mdseg
+
+extern "C" size_t mdseg_proj_bwd_graph_tc_workspace_bytes(const mdseg_graph_table* graphs, int n_images, int h, int w) {
+  using namespace mdseg;
+  if (!graphs || graphs->C_uni <= 0 || n_images <= 0 || h <= 0 || w <= 0) return 256;
+  const int n_slabs = dg_slabs(n_images, (long long)h * w);
+  return (size_t)n_images * 2 * n_slabs * kDgM * pad16(graphs->C_uni) * 4 + 512;
+}
+
+extern "C" int mdseg_proj_bwd_graph_tc(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,
+                                       const mdseg_graph_table* graphs, const int32_t* dataset_ids, int n_images, int h,
+                                       int w, float* dG, long long dg_stride, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(graphs && graphs->n_datasets > 0 && graphs->n_datasets <= MDSEG_MAX_DATASETS && graphs->C_uni > 0,
+                "mdseg_proj_bwd_graph_tc: bad graph table");
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && h > 0 && w > 0, "mdseg_proj_bwd_graph_tc: bad shape");
+  MDSEG_REQUIRE(is_float_dtype(dtype), "mdseg_proj_bwd_graph_tc: unsupported dtype %d", dtype);
+  if (n_images == 0) return 0;
+  MDSEG_REQUIRE(x && dyA && dG && workspace, "mdseg_proj_bwd_graph_tc: null pointer");
+  MDSEG_REQUIRE(workspace_bytes >= mdseg_proj_bwd_graph_tc_workspace_bytes(graphs, n_images, h, w),
+                "mdseg_proj_bwd_graph_tc: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+
+  DgArgs a;
+  a.x = x; a.dyA = dyA; a.dyB = dyB; a.dataset_ids = dataset_ids;
+  a.part = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  a.n_datasets = graphs->n_datasets; a.C_uni = graphs->C_uni; a.npad = pad16(graphs->C_uni); a.y_cmax = y_cmax;
+  a.hw = (long long)h * w;
+  a.n_slabs = dg_slabs(n_images, a.hw);
+  a.slab = ((a.hw + a.n_slabs - 1) / a.n_slabs + kKB - 1) / kKB * kKB;  // whole chunks, 32-pixel aligned starts
+  a.n_slabs = (int)((a.hw + a.slab - 1) / a.slab);
+  a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  const int terms = terms_of(dtype);
+  a.tc_mask = 0;
+  int cmax = 0;
+  for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
+    a.C_ds[i] = i < graphs->n_datasets ? graphs->g[i].C_ds : 0;
+    if (i < graphs->n_datasets && dg_dataset(graphs->g[i], graphs->C_uni)) {
+      MDSEG_REQUIRE(y_cmax >= graphs->g[i].C_ds, "mdseg_proj_bwd_graph_tc: y_cmax %d < C_ds %d", y_cmax, graphs->g[i].C_ds);
+      MDSEG_REQUIRE(dg_stride >= (long long)graphs->g[i].C_ds * graphs->C_uni, "mdseg_proj_bwd_graph_tc: dg_stride too small");
+      a.tc_mask |= 1u << i;
+      cmax = graphs->g[i].C_ds > cmax ? graphs->g[i].C_ds : cmax;
+    }
+  }
+  // everything outside the tensor-core envelope: the FFMA kernel of proj.cu
+  if (int rc = proj_dgraph_rest(x, dtype, dyA, dyB, y_cmax, graphs, dataset_ids, n_images, h, w, dG, dg_stride, a.tc_mask, s))
+    return rc;
+  if (!a.tc_mask) return 0;
+
+  a.a_stage_bytes = terms * 4 * kDgM * 16;
+  a.b_stage_bytes = terms * 4 * a.npad * 16;
+  const size_t smem = (size_t)kStagesTc * (a.a_stage_bytes + a.b_stage_bytes);
+  MDSEG_REQUIRE(smem <= 220 * 1024, "mdseg_proj_bwd_graph_tc: C_uni too large for the staged operands");
+  const dim3 grid((unsigned)a.n_slabs, 2u, (unsigned)n_images);
+  const dim3 rgrid((unsigned)(((long long)cmax * a.C_uni + 255) / 256), (unsigned)graphs->n_datasets);
+#define MDSEG_DG_LAUNCH(T, TERMS)                                                                       \
+  do {                                                                                                  \
+    auto k = proj_tc_dgraph_kernel<T, TERMS>;                                                           \
+    MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k<<<grid, kTcThreads, smem, s>>>(a);                                                                \
+    MDSEG_LAUNCH_OK();                                                                                  \
+  } while (0)
+  switch (dtype) {
+    case MDSEG_F32: MDSEG_DG_LAUNCH(float, 3); break;
+    case MDSEG_BF16: MDSEG_DG_LAUNCH(__nv_bfloat16, 1); break;
+    case MDSEG_F16: MDSEG_DG_LAUNCH(__half, 1); break;
+  }
+#undef MDSEG_DG_LAUNCH
+  proj_tc_dgraph_reduce_kernel<<<rgrid, 256, 0, s>>>(a, n_images, dG, dg_stride);
+  MDSEG_LAUNCH_OK();
+  return 0;
+}

@@ -96,6 +96,9 @@ SIGNATURES = {
     "mdseg_proj_bwd_tc_workspace_bytes": (C.c_size_t, [C.POINTER(GraphTable), _I]),
     "mdseg_proj_bwd_tc": (_I, [_P, _P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, _I, _P, C.c_size_t, _P]),
     "mdseg_proj_bwd_graph": (_I, [_P, _I, _P, _P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, C.c_longlong, _P]),
+    "mdseg_proj_bwd_graph_tc_workspace_bytes": (C.c_size_t, [C.POINTER(GraphTable), _I, _I, _I]),
+    "mdseg_proj_bwd_graph_tc": (_I, [_P, _I, _P, _P, _I, C.POINTER(GraphTable), _P, _I, _I, _I, _P, C.c_longlong, _P,
+                                     C.c_size_t, _P]),
     "mdseg_up_ce_fwd": (_I, [C.POINTER(SrcTable), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mdseg_up_ce_bwd": (_I, [C.POINTER(SrcTable), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F,
                              C.POINTER(SrcTable), C.POINTER(SrcTable), _P]),

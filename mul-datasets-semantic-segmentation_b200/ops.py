@@ -613,8 +613,14 @@ class _MdsProjOhemCE(torch.autograd.Function):
         if want_dg:
             stride = cmax * Cu
             dG = torch.zeros(n, stride, dtype=torch.float32, device=dev)
-            N.call("mdseg_proj_bwd_graph", _ptr(x), _DT[x.dtype], _ptr(dyA), _ptr(dyB), cmax, C.byref(tab), _ptr(ids),
-                   B, h, w, _ptr(dG), stride, _stream())
+            if any(tab.g[i].dense for i in range(tab.n_datasets)):  # dense graphs: split-K GEMM on the tensor cores
+                nb = N.lib.mdseg_proj_bwd_graph_tc_workspace_bytes(C.byref(tab), B, h, w)
+                ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+                N.call("mdseg_proj_bwd_graph_tc", _ptr(x), _DT[x.dtype], _ptr(dyA), _ptr(dyB), cmax, C.byref(tab),
+                       _ptr(ids), B, h, w, _ptr(dG), stride, _ptr(ws), nb, _stream())
+            else:
+                N.call("mdseg_proj_bwd_graph", _ptr(x), _DT[x.dtype], _ptr(dyA), _ptr(dyB), cmax, C.byref(tab),
+                       _ptr(ids), B, h, w, _ptr(dG), stride, _stream())
             for i in range(n):
                 if ctx.needs_input_grad[6 + i]:
                     dgs[i] = dG[i, :Cs[i] * Cu].view(Cs[i], Cu).to(graphs[i].dtype)
