@@ -365,6 +365,9 @@ int mdseg_mds_bwd(const mdseg_src_table* src /*host*/, const mdseg_graph_table* 
  * Sources must be fp32 on the fused route; other cases take the two-plane route inside the workspace. */
 size_t mdseg_up_ce_bwd_direct_workspace_bytes(const mdseg_src_table* src /*host*/, int n_images, int h, int w, int H,
                                               int W);
+/* 1 when mdseg_up_ce_bwd_direct takes the fused single-pass kernel for this source table and geometry (fp32
+ * sources, aligned rows, up-sampling factor <= 5): destinations may then have any image stride. */
+int mdseg_up_ce_bwd_direct_is_fused(const mdseg_src_table* src /*host*/, int h, int w, int H, int W);
 int mdseg_up_ce_bwd_direct(const mdseg_src_table* src /*host*/, const int32_t* dataset_ids, const void* labels,
                            int label_dtype, int n_images, int h, int w, int H, int W, int ignore,
                            const float* loss_px, const float* lse_px, mdseg_ohem_state* states,

@@ -743,6 +743,13 @@ extern "C" size_t mdseg_up_ce_bwd_direct_workspace_bytes(const mdseg_src_table* 
   return planes + 256;
 }
 
+extern "C" int mdseg_up_ce_bwd_direct_is_fused(const mdseg_src_table* src, int h, int w, int H, int W) {
+  using namespace mdseg;
+  if (!src || src->n_datasets <= 0 || src->n_datasets > MDSEG_MAX_DATASETS || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
+  const Geom gm = geom_of(h, w, H, W);
+  return (gm.W % 16 == 0 && tma::fast_geometry(*src, gm)) ? 1 : 0;
+}
+
 extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t* dataset_ids, const void* labels,
                                       int label_dtype, int n_images, int h, int w, int H, int W, int ignore,
                                       const float* loss_px, const float* lse_px, mdseg_ohem_state* states,

@@ -106,6 +106,7 @@ SIGNATURES = {
     "mdseg_mds_bwd": (_I, [C.POINTER(SrcTable), C.POINTER(GraphTable), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P,
                            _P, _F, _P, _I, _P, C.c_size_t, _P]),
     "mdseg_up_ce_bwd_direct_workspace_bytes": (C.c_size_t, [C.POINTER(SrcTable), _I, _I, _I, _I, _I]),
+    "mdseg_up_ce_bwd_direct_is_fused": (_I, [C.POINTER(SrcTable), _I, _I, _I, _I]),
     "mdseg_up_ce_bwd_direct": (_I, [C.POINTER(SrcTable), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F,
                                     C.POINTER(SrcTable), _P, C.c_size_t, _P]),
     "mdseg_add_planes": (_I, [_P, _P, _P, _I, _L, _P]),

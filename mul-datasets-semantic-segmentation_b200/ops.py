@@ -592,12 +592,22 @@ class _MdsProjOhemCE(torch.autograd.Function):
                        w, H, W, ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, _ptr(dx), _DT[x.dtype],
                        _ptr(ws), nbytes, _stream())
             return (dx, None, None, None, None, None, *([None] * n))
-        dyA = torch.empty_like(y)
-        dyB = torch.empty_like(y)
-        dA = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
-        dB = _src_table([dyB.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
-        N.call("mdseg_up_ce_bwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, ignore,
-               _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dA), C.byref(dB), _stream())
+        if N.lib.mdseg_up_ce_bwd_direct_is_fused(C.byref(src), h, w, H, W):
+            # the fused single-pass kernel with the identity in place of G^T: one gradient plane d loss / d y
+            dyA, dyB = torch.empty_like(y), None  # only the first C_ds planes of an image are written — and read
+            dst = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+            nbytes = N.lib.mdseg_up_ce_bwd_direct_workspace_bytes(C.byref(src), B, h, w, H, W)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            N.call("mdseg_up_ce_bwd_direct", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W,
+                   ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dst), _ptr(ws), nbytes,
+                   _stream())
+        else:
+            dyA = torch.empty_like(y)
+            dyB = torch.empty_like(y)
+            dA = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+            dB = _src_table([dyB.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
+            N.call("mdseg_up_ce_bwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, ignore,
+                   _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dA), C.byref(dB), _stream())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
