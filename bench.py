@@ -62,6 +62,10 @@ def parse():
     ap.add_argument("--eager-gpu", action="store_true",
                     help="also time the reference's own torch op sequence (oracle/torch_ref.py, the same code as the "
                          "CPU baseline) on CUDA tensors on this GPU: PyTorch eager, reported as 'reference_eager_gpu'")
+    ap.add_argument("--bi-graphs", default="onehot", choices=["onehot", "dense"],
+                    help="onehot: 0/1 column-one-hot graphs (SEG stage, the headline).  dense: soft trainable graphs "
+                         "softmax(randn * 4) with requires_grad (GNN stage): projection, adjoint and d bi_graph run on "
+                         "the tcgen05 tensor cores; not the headline config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
     return ap.parse_args()
@@ -166,7 +170,7 @@ class Clocks(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL = {"mdseg_up_ce_bwd_direct": 3,
+KERNELS_PER_CALL = {"mdseg_up_ce_bwd_direct": 3, "mdseg_proj_fwd_tc": 2, "mdseg_proj_bwd_tc": 3, "mdseg_proj_bwd_graph_tc": 2,
                     "mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
                     "mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
                     "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
@@ -203,6 +207,10 @@ def run_ours(args, rank, world, local_rank):
     px = B * H * W
     lab_dt = torch.int64 if args.label_dtype == "int64" else torch.uint8
     graphs = [g.to(dev) for g in bt["graphs"]]
+    if args.bi_graphs == "dense":  # GNN stage: soft adjacency with grad (loss_cross_datasets.py:997-1006)
+        ggen = torch.Generator(device=dev).manual_seed(7)
+        graphs = [torch.softmax(torch.randn(c, bt["c_uni"], generator=ggen, device=dev) * 4, dim=0).requires_grad_(True)
+                  for c in n_cats]
     luts = torch.from_numpy(np.stack(bt["luts"])).to(dev)  # [n_datasets, 256]
     ids_t = torch.tensor(ids, dtype=torch.int32, device=dev)
     slices = dataset_slices(ids)
@@ -235,6 +243,8 @@ def run_ours(args, rank, world, local_rank):
         main = torch.cuda.current_stream()
         # a5-a9: fused projection + upsample + OhemCE fwd, selection, bwd
         xin.grad = None
+        for gph in graphs:
+            gph.grad = None
         loss = ops.mds_proj_ohem_ce(xin, labels, ids_t, graphs, thresh)
         if aux is not None:
             for t in aux:
@@ -349,6 +359,10 @@ def run_ours(args, rank, world, local_rank):
             "mdseg_up_ce_bwd": cbar * 4 / 16 + L + 8 + 2 * cbar * 4 / 16,
             "mdseg_proj_bwd": (2 * cbar * 4 + cu * e) / 16,
             "mdseg_mds_bwd": cbar * 4 / 16 + L + 8 + cu * e / 16,
+            "mdseg_proj_fwd_tc": (cu * e + cbar * 4) / 16,
+            "mdseg_up_ce_bwd_direct": cbar * 4 / 16 + L + 8 + cbar * 4 / 16,
+            "mdseg_proj_bwd_tc": (cbar * 4 + cu * e) / 16,
+            "mdseg_proj_bwd_graph_tc": (cbar * 4 + cu * e) / 16,
             "mdseg_lut_remap": 1 + L,
             "mdseg_confusion": L + 8,
             "mdseg_lut_remap_images": 1 + L,
@@ -362,6 +376,16 @@ def run_ours(args, rank, world, local_rank):
                 gbs = alg[name] * px / (tot * 1e-3) / 1e9
                 per_kernel[name].update({"alg_bytes_per_px": round(alg[name], 3), "achieved_gbs": round(gbs, 1),
                                          "frac": round(gbs / peak, 4)})
+        # the three tensor-core calls of the GNN stage: useful FLOP = 2 * C_uni * C_ds per low-res pixel each
+        tf_peak = None
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
+        for name in ("mdseg_proj_fwd_tc", "mdseg_proj_bwd_tc", "mdseg_proj_bwd_graph_tc"):
+            if name in per_kernel:
+                tfl = 2.0 * cu * cbar * (px / 16) / (per_kernel[name]["ms_per_step"] * 1e-3) / 1e12
+                per_kernel[name]["useful_tflops"] = round(tfl, 1)
+                if tf_peak:
+                    per_kernel[name]["frac_of_bf16_peak"] = round(tfl / tf_peak, 4)
         cand = {k: v for k, v in per_kernel.items() if "achieved_gbs" in v}
         if cand:
             top = max(cand, key=lambda k: cand[k]["ms_per_step"])
@@ -375,7 +399,8 @@ def run_ours(args, rank, world, local_rank):
         # whole group A (3*C_uni*e/16 + 2L + 20 bytes per pixel) and B (L + 8)
         grpA = sum(per_kernel.get(k, {}).get("ms_per_step", 0) for k in
                    ("mdseg_proj_fwd", "mdseg_up_ce_fwd", "mdseg_ohem_begin", "mdseg_ohem_select", "mdseg_up_ce_bwd",
-                    "mdseg_proj_bwd", "mdseg_mds_bwd"))
+                    "mdseg_proj_bwd", "mdseg_mds_bwd", "mdseg_proj_fwd_tc", "mdseg_up_ce_bwd_direct",
+                    "mdseg_proj_bwd_tc", "mdseg_proj_bwd_graph_tc"))
         bytesA = 3 * cu * e / 16 + 2 * L + 20
         if grpA:
             per_kernel["group_A_loss_fwd_select_bwd"] = {
@@ -392,7 +417,9 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD_NAMES[args.workload], "name": args.workload,
                        "pixels_per_step_per_gpu": px, "labels": args.label_dtype,
                        "logits": f"{args.logits_dtype} NCHW (CE arithmetic fp32)",
-                       "bi_graphs": "0/1 column-one-hot (SEG stage)", "ohem_thresh": 0.4,
+                       "bi_graphs": "0/1 column-one-hot (SEG stage)" if args.bi_graphs == "onehot" else
+                                    "dense fp32 softmax graphs with grad (GNN stage; tcgen05 projection, adjoint, d bi_graph)",
+                       "ohem_thresh": 0.4,
                        "aux_heads": bool(args.with_aux),
                        "l2": "inputs_exceed_l2 (logits %.2f GB, labels+preds %.2f GB per step)" %
                              (bt["x"].numel() * bt["x"].element_size() / 1e9, px * (1 + (8 if lab_dt == torch.int64 else 1) + 8) / 1e9),
