@@ -299,25 +299,43 @@ def run_ours(args, rank, world, local_rank):
     h_x = bt["x"].detach().cpu().pin_memory()
     h_raw = bt["raw"].cpu().pin_memory()
     h_pred = bt["pred"].cpu().pin_memory()
-    d_x = torch.empty_like(bt["x"].detach()).requires_grad_(True)
-    d_raw, d_pred = torch.empty_like(bt["raw"]), torch.empty_like(bt["pred"])
+    # two device input sets: the host->device copies of step i + 1 run on a copy stream beside the kernels of step i
+    # (what a data loader with a prefetch queue does); every timed step still copies its own inputs and reads its
+    # own results back, and the timed region contains exactly e2e_steps copies and e2e_steps computations.
+    bufs = []
+    for _ in range(2):
+        bufs.append((torch.empty_like(bt["x"].detach()).requires_grad_(True), torch.empty_like(bt["raw"]),
+                     torch.empty_like(bt["pred"]), torch.cuda.Event()))
     h2d = h_x.numel() * h_x.element_size() + h_raw.numel() + h_pred.numel() * 8
     d2h = 4 + 4 * len(n_cats)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
 
-    def e2e_step():
-        with torch.no_grad():
+    def issue_copy(slot):
+        d_x, d_raw, d_pred, ready = bufs[slot]
+        copy_stream.wait_stream(main_stream)  # the buffers' previous consumer (two steps ago) has been enqueued
+        with torch.cuda.stream(copy_stream), torch.no_grad():
             d_x.copy_(h_x, non_blocking=True)
-        d_raw.copy_(h_raw, non_blocking=True)
-        d_pred.copy_(h_pred, non_blocking=True)
+            d_raw.copy_(h_raw, non_blocking=True)
+            d_pred.copy_(h_pred, non_blocking=True)
+            ready.record(copy_stream)
+
+    def e2e_step(i, prefetch_next):
+        d_x, d_raw, d_pred, ready = bufs[i % 2]
+        main_stream.wait_event(ready)
+        if prefetch_next:
+            issue_copy((i + 1) % 2)
         step(d_raw, d_x, d_pred)
         return float(out["loss"].cpu()), out["miou"].cpu()
 
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    issue_copy(0)
+    e2e_step(0, False)  # warm-up
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    issue_copy(1)  # pipeline fill: the first timed step waits for its own copy
+    for i in range(1, e2e_steps + 1):
+        e2e_step(i, i < e2e_steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -325,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = px * world / (float(t.item()) / e2e_steps * 1e-3)
     clk = clocks.summary() if clocks else None  # sampled over the device-resident and the end-to-end timed loops
-    del h_x, d_x
+    del h_x, bufs
 
     # ---- per-kernel durations (separate loop, L2 flushed between launches) -> roofline -------------------
     peak, peak_src = measured_peak()
@@ -424,7 +442,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "inputs_exceed_l2 (logits %.2f GB, labels+preds %.2f GB per step)" %
                              (bt["x"].numel() * bt["x"].element_size() / 1e9, px * (1 + (8 if lab_dt == torch.int64 else 1) + 8) / 1e9),
                        "parallelism": f"dp{world} (images sharded, OHEM selection rank-local, one int64 hist all-reduce)",
-                       "streams": "loss fwd/select/bwd on the main stream, confusion matrices + all-reduce + mIoU on a side stream"},
+                       "streams": "loss fwd/select/bwd on the main stream, confusion matrices + all-reduce + mIoU on a side stream; "
+                                  "e2e: host->device copies of step i+1 on a copy stream beside step i"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": gpu_launches, "clocks": clk, "loss": loss_val,
