@@ -88,3 +88,83 @@ class MscEvalV0:
                 acc.update_from_passes(label[b], per_image[b])
         acc.all_reduce()
         return acc.miou()
+
+
+class MscEvalV0_Contrast:
+    """evaluate.py:101-192 — the evaluator ``eval_model_contrast`` (:1127) and tools/eval_snp.py build as
+    ``MscEvalV0_Contrast(configer, (0.5,), False)``.  The net returns the logits tensor itself.  With
+    ``ori_scales=False`` (the default) the probabilities stay at the resolution of the logits and the *label* is
+    resized to it with torch's legacy 'nearest' rule, once per scale and cumulatively (:156-157); with
+    ``ori_scales=True`` the logits are up-sampled to the label as in ``MscEvalV0``."""
+
+    def __init__(self, configer, scales=(0.5,), flip=False, ignore_label=255, ori_scales=False):
+        self.configer, self.scales, self.flip = configer, scales, flip
+        self.ignore_label, self.ori_scales = ignore_label, ori_scales
+
+    @torch.no_grad()
+    def __call__(self, net, dl, n_classes, dataset_id):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        acc = SegHist(n_classes, dev, self.ignore_label)
+        for imgs, label in dl:
+            N_, _, H, W = label.shape
+            label = label.squeeze(1).to(dev, non_blocking=True)
+            per_image = [[] for _ in range(N_)]
+            psize = (H, W)
+            for scale in self.scales:
+                sH, sW = get_round_size((int(scale * H), int(scale * W)))
+                im_sc = F.interpolate(imgs, size=(sH, sW), mode='bilinear', align_corners=True).to(dev)
+                logits = net(im_sc, dataset=dataset_id)
+                lH, lW = logits.shape[-2:]
+                if not self.ori_scales:
+                    if per_image[0] and psize != (lH, lW):
+                        # the reference's `probs += softmax(logits)` fails on the shape mismatch here (:163)
+                        raise RuntimeError(f"ori_scales=False: logits of size {(lH, lW)} after probabilities of size {psize}")
+                    label = ops.label_nearest(label, (lH, lW))
+                    psize = (lH, lW)
+                for b in range(N_):
+                    per_image[b].append((logits[b], False))
+                if self.flip:
+                    if psize != (H, W):
+                        raise RuntimeError("ori_scales=False with flip: the reference up-samples the flipped pass to the "
+                                           "label size (:169) and fails on the shape mismatch")
+                    logits = net(torch.flip(im_sc, dims=(3,)), dataset=dataset_id)
+                    for b in range(N_):
+                        per_image[b].append((logits[b], True))
+            for b in range(N_):
+                acc.update_from_passes(label[b], per_image[b])
+        acc.all_reduce()
+        return acc.miou()
+
+
+class MscEvalV0_AutoLink:
+    """evaluate.py:582-640 — rectangular ``[n_classes, n_cats_k]`` confusion matrices of this dataset's labels
+    against the arg-max of every *other* dataset's head (first scale only, no flip); returns, per dataset, the
+    row arg-max (identity rows for the dataset itself)."""
+
+    def __init__(self, configer, scales=(0.5,), flip=False, ignore_label=255):
+        self.configer, self.n_datasets = configer, configer.get('n_datasets')
+        self.scales, self.flip, self.ignore_label = scales, flip, ignore_label
+
+    @torch.no_grad()
+    def __call__(self, net, dl, n_classes, dataset_id):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        n_cats = [self.configer.get('dataset' + str(k + 1), 'n_cats') for k in range(self.n_datasets)]
+        hists = [None if k == dataset_id else torch.zeros(n_classes, n_cats[k], dtype=torch.int64, device=dev)
+                 for k in range(self.n_datasets)]
+        scale = self.scales[0]
+        for imgs, label in dl:
+            N_, _, H, W = label.shape
+            label = label.squeeze(1).to(dev, non_blocking=True)
+            sH, sW = get_round_size((int(scale * H), int(scale * W)))
+            im_sc = F.interpolate(imgs, size=(sH, sW), mode='bilinear', align_corners=True).to(dev)
+            all_logits = net(im_sc)
+            for k in range(self.n_datasets):
+                if k == dataset_id:
+                    continue
+                for b in range(N_):
+                    # softmax is monotone: arg-max of the up-sampled logits through the one-pass fused kernel
+                    pred = ops.eval_fused([(all_logits[k][b], False)], (H, W))[0]
+                    ops.confusion(label[b], pred, n_classes, n_cats[k], ignore=self.ignore_label, hist=hists[k])
+        ops.check_errors(dev)
+        eye = torch.eye(n_classes, device=dev)
+        return [torch.argmax(eye if h is None else h, dim=1) for h in hists]

@@ -397,6 +397,12 @@ class BipartiteGraphs:
             raise ValueError("bi_graph must be [C_ds, C_uni]")
         dev = g.device
         ent = {"key": key, "tensor": g, "C_ds": g.shape[0], "C_uni": g.shape[1]}
+        if g.requires_grad:
+            # trainable graph (GNN stage): dense by definition, decided without copying it to the host —
+            # it changes every iteration and a D2H copy per graph per step would serialise the stream
+            ent["dense"], ent["nnz"] = True, g.shape[0] * g.shape[1]
+            self._cache[i] = ent
+            return ent
         m = g.detach().to(torch.float32).cpu().numpy()
         nz = m != 0
         nnz = int(nz.sum())

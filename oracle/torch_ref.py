@@ -93,6 +93,45 @@ def seg_stage_total_loss(logits_uni, aux_logits, labels, dataset_ids, bi_graphs,
     return main + aux_weight * aux, main, aux
 
 
+def gnn_stage_total_loss(feats, unify_prototype, bi_graphs, labels, dataset_ids, n_cats, max_rate,
+                         target_bi_graph=None, temperature=0.07, orth_weight=1.0, aux_weight=0.2, adj_loss_weight=1.0):
+    """CrossDatasetsCELoss_AdvGNN.forward in the GNN stage the ltbgnn configs drive (is_adv=True, dataset aux heads,
+    2*n graphs = (hard, soft) pairs, with_orth, mse_or_adv "None"; loss_cross_datasets.py:941-1136):
+      aux_i   = OhemCE(0.7)(upsample(einsum(feats[ids==i], proto[cur:cur+n_i])), target[ids==i])        (:941-951,:1047)
+      logits  = einsum(feats, proto[total:])                                                              (:961)
+      orth    = orth_weight * (-mean(softmax(P P^T / T) * log_softmax(P P^T / T))), P = proto[total:]     (:977-980)
+      adj     = sum_i (1/C_uni) * sum-squared-error(soft_i, target_i) where target_i != 255                (:1030-1043)
+      ce      = max_rate * MdsOhemCE(0.4)(hard graphs) + (1 - max_rate) * MdsOhemCE(0.4)(soft graphs)     (:1063-1071)
+      loss    = ce + aux_weight * sum aux_i + orth + adj_loss_weight * adj                                 (:1129-1136)
+    Returns (loss, orth, aux, adj)."""
+    n = len(n_cats)
+    total = sum(n_cats)
+    size = (labels.size(1), labels.size(2))
+    aux, adj, cur = None, None, 0
+    for i in range(n):
+        sel = dataset_ids == i
+        if sel.any():
+            head = upsample(project(feats[sel], unify_prototype[cur:cur + n_cats[i]]), size)
+            li = ohem_ce_loss(head, labels[sel], 0.7)
+            aux = li if aux is None else aux + li
+            if target_bi_graph is not None:
+                keep = target_bi_graph[i] != 255
+                soft = bi_graphs[2 * i + 1]
+                li = (1 / soft.shape[1]) * F.mse_loss(soft[keep], target_bi_graph[i][keep], reduction="sum")
+                adj = li if adj is None else adj + li
+        cur += n_cats[i]
+    proto = unify_prototype[total:]
+    logits = project(feats, proto)
+    z = torch.mm(proto, proto.t()) / temperature
+    orth = orth_weight * (-1 * torch.mean(F.softmax(z, dim=1) * F.log_softmax(z, dim=1)))
+    ce = (max_rate * multi_dataset_seg_loss(logits, labels, dataset_ids, bi_graphs[0::2])
+          + (1 - max_rate) * multi_dataset_seg_loss(logits, labels, dataset_ids, bi_graphs[1::2]))
+    loss = ce + aux_weight * aux + orth
+    if adj is not None:
+        loss = loss + adj_loss_weight * adj
+    return loss, orth, aux, adj
+
+
 def remap_matrix_ce_loss(logits, labels, dataset_ids, remap_matrices, ignore=IGNORE):
     """CrossDatasetsCELoss.forward (loss_cross_datasets.py:323-347): per dataset plain mean CE of the
     remap-matrix projection, summed — the path the reference's golden value 5.106813430786133 pins."""

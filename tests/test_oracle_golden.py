@@ -208,3 +208,84 @@ def test_confusion_miou_restatement():
     assert np.isnan(ious[1]) and miou == 1.0
     with pytest.raises(ValueError):
         ls.confusion(np.array([5]), np.array([0]), 3)
+
+
+# ---- evaluator tail pinned on the REAL evaluate.py (tests/golden/make_golden_eval.py) -----------------------
+def _eval_case(z, tag):
+    labels = [torch.from_numpy(z[f"{tag}_label{i}"].astype(np.int64)) for i in range(int(z[f"{tag}_n_batches"]))]
+    calls = [[torch.from_numpy(z[f"{tag}_call{i}_head0"])] for i in range(int(z[f"{tag}_n_calls"]))]
+    hists = [z[f"{tag}_hist{i}"] for i in range(int(z[f"{tag}_n_hists"]))]
+    return labels, calls, hists
+
+
+@pytest.mark.parametrize("tag,n_scales,flip,ori", [("v0", 6, True, True), ("c_ori", 2, True, True),
+                                                   ("c_low", 1, False, False), ("absent", 1, False, True)])
+def test_evaluator_restatement_against_real_evaluate_py(golden, tag, n_scales, flip, ori):
+    """oracle.torch_ref.eval_probs / eval_preds / nearest_label + oracle.label_space.confusion / ious_miou replay
+    the logits the real MscEvalV0 / MscEvalV0_Contrast saw and must give their np.bincount results and mIoU."""
+    z = golden("evaluator.npz")
+    labels, calls, hists = _eval_case(z, tag)
+    per_batch = n_scales * (2 if flip else 1)
+    assert len(calls) == per_batch * len(labels) and len(hists) == len(labels)
+    total = None
+    for b, lb in enumerate(labels):
+        passes = [c[0] for c in calls[b * per_batch:(b + 1) * per_batch]]
+        flips = [bool(flip and (i % 2)) for i in range(per_batch)]
+        lab = lb.squeeze(1)
+        if ori:
+            size = tuple(lab.shape[-2:])
+        else:
+            size = tuple(passes[0].shape[-2:])
+            lab = tr.nearest_label(lab, size)
+            assert np.array_equal(lab.numpy(), ls.nearest_resize(lb.squeeze(1).numpy(), size))
+        pred = tr.eval_preds(tr.eval_probs(passes, size, flips))
+        C = passes[0].shape[1]
+        h = ls.confusion(lab.numpy(), pred.numpy(), C)
+        assert np.array_equal(h.reshape(-1), hists[b])
+        total = h if total is None else total + h
+    assert abs(ls.ious_miou(total)[1] - float(z[f"{tag}_miou"])) <= 1e-7
+
+
+def test_autolink_rectangular_hist_against_real_evaluate_py(golden):
+    """evaluate.py:582-640: [n_classes, n_cats_k] histograms against the other datasets' heads, row arg-max."""
+    z = golden("evaluator.npz")
+    n_cats, me = [19, 12, 36], 1
+    nb = int(z["autolink_n_batches"])
+    tot = {k: np.zeros((n_cats[me], n_cats[k]), dtype=np.int64) for k in range(3) if k != me}
+    hi = 0
+    for b in range(nb):
+        lab = z[f"autolink_label{b}"].astype(np.int64).squeeze(1)
+        for k in tot:
+            lg = torch.from_numpy(z[f"autolink_call{b}_head{k}"])
+            pred = tr.eval_preds(tr.eval_probs([lg], lab.shape[-2:]))
+            h = ls.confusion(lab, pred.numpy(), n_cats[me], n_cats[k])
+            assert np.array_equal(h.reshape(-1), z[f"autolink_hist{hi}"])
+            hi += 1
+            tot[k] += h
+    assert hi == int(z["autolink_n_hists"])
+    for k in range(3):
+        want = z[f"autolink_argmax{k}"]
+        got = np.arange(n_cats[me]) if k == me else tot[k].argmax(axis=1)
+        assert np.array_equal(got, want)
+
+
+def test_advgnn_gnn_stage_golden(golden):
+    """CrossDatasetsCELoss_AdvGNN of the real reference in the GNN stage (tests/golden/make_golden_gnn_stage.py):
+    prototype head, (hard, soft) graph pairs blended by max_rate, aux heads from the prototypes, orth + adj terms."""
+    z = golden("advgnn_gnn_stage.npz")
+    n_cats = [19, 64, 37, 19, 26, 150, 133]
+    feats = torch.from_numpy(z["feats"]).requires_grad_(True)
+    proto = torch.from_numpy(z["proto"]).requires_grad_(True)
+    graphs = [torch.from_numpy(z[f"graph{i}"]).requires_grad_(True) for i in range(14)]
+    tgt = [torch.from_numpy(z[f"target{i}"]) for i in range(7)]
+    loss, orth, aux, adj = tr.gnn_stage_total_loss(feats, proto, graphs, torch.from_numpy(z["labels"].astype(np.int64)),
+                                                   torch.from_numpy(z["ids"]), n_cats, 21000 / 60000, tgt)
+    for got, key in ((loss, "loss"), (orth, "orth"), (aux, "aux"), (adj, "adj")):
+        assert abs(float(got) - float(z[key])) <= 2e-6 * abs(float(z[key])), key
+    loss.backward()
+    assert np.abs(feats.grad.numpy() - z["dfeats"]).max() <= 1e-6 * np.abs(z["dfeats"]).max()
+    assert np.abs(proto.grad.numpy() - z["dproto"]).max() <= 1e-6 * np.abs(z["dproto"]).max()
+    for i in range(14):
+        want = z[f"dgraph{i}"]
+        got = graphs[i].grad.numpy() if graphs[i].grad is not None else np.zeros_like(want)
+        assert np.abs(got - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30), i
