@@ -21,6 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-I", INCLUDE]
+CFLAGS += os.environ.get("MDSEG_CFLAGS", "").split()  # experiment switches (-DMDSEG_...=k); empty in normal builds
 
 
 def _sources():

@@ -13,7 +13,7 @@
 //   the strip width is a multiple of four columns so that finished rows leave as 16-byte stores.
 //   * the class planes of rows (g, g+1) arrive as 4-D TMA boxes [16 classes][2 rows][36 cols]
 //     in a 3-stage mbarrier ring (lane 0 issues, nobody copies);
-//   * per (pixel, class): w*softmax = ex2(z2 - (lse2 - log2 w)), with the 4..5 x 4..5 label pixels
+//   * per (pixel, class): w*softmax = ex2(z*log2e + (log2 w - lse2)), with the 4..5 x 4..5 label pixels
 //     of the cell in registers and the arithmetic packed two columns per instruction (FFMA2/FADD2);
 //     per class the cell reduces to 4 sums (upper/lower row x own/right column); the right-column
 //     part moves one lane up by shuffle;
@@ -55,7 +55,6 @@ struct GraphDev {
 
 struct Args {
   mdseg_src_table src;
-  int src_scaled;  // sources already multiplied by log2(e)
   const int32_t* dataset_ids;
   const void* labels;
   Geom gm;
@@ -72,7 +71,7 @@ struct Args {
   int zero_invalid;  // images with an out-of-range dataset id get zeros in out_base[0]
   float* scrA;       // [n_images][n_seg][c_scr][w]: upper-row half of the first row of a segment
   float* scrB;       // same shape: lower-row half left over by the segment above
-  float* lw2;        // [n_images*H*W]: lse*log2e - log2|w| for pixels with a gradient, +inf otherwise
+  float* lw2;        // [n_images*H*W]: log2|w| - lse*log2e for pixels with a gradient, -inf otherwise
   uint8_t* sel8;     // [n_images*H*W]: class of the pixel, 255 = no gradient
   int c_scr;
   int seg_rows, n_seg, n_strips;
@@ -127,7 +126,7 @@ __global__ void __launch_bounds__(256) mds_bwd_prep_kernel(const Args a, int64_t
     for (int i = 0; i < 4; ++i) {
       const int lv = load_label<L>(labels, p + i);
       const bool sel = (lv != a.ignore) && ((unsigned)lv < (unsigned)C) && (wabs > 0.f) && is_selected(sp, lsv[i]);
-      o[i] = sel ? fmaf(lev[i], kLog2e, -log2w) : kInf;
+      o[i] = sel ? fmaf(-lev[i], kLog2e, log2w) : -kInf;
       packed |= (sel ? (uint32_t)lv : 255u) << (8 * i);
     }
     *reinterpret_cast<float4*>(a.lw2 + p) = make_float4(o[0], o[1], o[2], o[3]);
@@ -230,7 +229,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     uint32_t hv[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-      t[i] = kInf;
+      t[i] = -kInf;
       hv[i] = 255u;
       if (j < R && i < un.nx) {
         t[i] = lw2s[j * kStgW + un.sx + i];
@@ -257,6 +256,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
   // first column of the strip in row g of channel 0
   TO* orow = outb + (int64_t)g * a.gm.w + un.x0;
   const float nwabs = -fabsf(un.w_signed);
+  const float2 K2 = dup2(kLog2e);  // natural-log logits -> base-2 exponent, folded into the offset FMA
 
 #pragma unroll 1
   for (int k = 0; k < un.n_ch; ++k) {
@@ -269,34 +269,32 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     const float* Sp = stages + slot * kStageFloats + un.xl;
     // corners of the next class are fetched while the current one is being computed (the loop stays rolled)
     float n00 = Sp[0], n01 = Sp[1], n10 = Sp[kBoxW], n11 = Sp[kBoxW + 1];
+    uint32_t c2 = class_pair(c_lo);
 #pragma unroll 1
-    for (int c = 0; c < cc; ++c) {
+    for (int c = 0; c < cc; ++c, c2 = next_class2(c2)) {
       float v00 = n00, v01 = n01, v10 = n10, v11 = n11;
       Sp += 2 * kBoxW;
       if (c + 1 < cc) { n00 = Sp[0]; n01 = Sp[1]; n10 = Sp[kBoxW]; n11 = Sp[kBoxW + 1]; }
-      if (!a.src_scaled) { v00 *= kLog2e; v01 *= kLog2e; v10 *= kLog2e; v11 *= kLog2e; }
       const float dv0 = v01 - v00, dv1 = v11 - v10;
       const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
-      float2 CU2 = make_float2(0.f, 0.f), UR2 = CU2, CL2 = CU2, LR2 = CU2;
-      const uint32_t ch = (uint32_t)__half_as_ushort(__int2half_rn(c_lo + c));
-      const uint32_t c2 = ch | (ch << 16);
+      float2 CU2, UR2, CL2, LR2;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const float2 h0 = fma2(L1W[p], DV0, V0);
         const float2 dd = sub2(fma2(L1W[p], DV1, V1), h0);
-        float2 t0 = make_float2(0.f, 0.f), t1 = t0;
+        float2 t0, t1;  // first terms assigned, not added to zero (x + 0 is not a no-op the compiler may drop)
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
-          float2 e = ex2_2(sub2(fma2(L1H[j], dd, h0), LW[j][p]));
+          float2 e = ex2_2(fma2(fma2(L1H[j], dd, h0), K2, LW[j][p]));
           sub_onehot2(e, LH[j][p], c2, nwabs);
-          t0 = add2(t0, e);
-          t1 = fma2(L1H[j], e, t1);
+          t0 = j == 0 ? e : add2(t0, e);
+          t1 = j == 0 ? mul2(L1H[j], e) : fma2(L1H[j], e, t1);
         }
         const float2 cu = sub2(t0, t1);
-        CU2 = add2(CU2, cu);
-        UR2 = fma2(L1W[p], cu, UR2);
-        CL2 = add2(CL2, t1);
-        LR2 = fma2(L1W[p], t1, LR2);
+        CU2 = p == 0 ? cu : add2(CU2, cu);
+        UR2 = p == 0 ? mul2(L1W[p], cu) : fma2(L1W[p], cu, UR2);
+        CL2 = p == 0 ? t1 : add2(CL2, t1);
+        LR2 = p == 0 ? mul2(L1W[p], t1) : fma2(L1W[p], t1, LR2);
       }
       float CU = CU2.x + CU2.y, ur = UR2.x + UR2.y, CL = CL2.x + CL2.y, lr = LR2.x + LR2.y;
       if (NX5) {
@@ -305,7 +303,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
         float t0 = 0.f, t1 = 0.f;
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
-          float2 e = make_float2(ex2_approx(fmaf(l1h[j], dd, h0) - lw4[j]), 0.f);
+          float2 e = make_float2(ex2_approx(fmaf(fmaf(l1h[j], dd, h0), kLog2e, lw4[j])), 0.f);
           sub_onehot2(e, lh4[j], c2, nwabs);
           t0 += e.x;
           t1 = fmaf(l1h[j], e.x, t1);
@@ -695,7 +693,7 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
   }
 
   Args a;
-  a.src = *src; a.src_scaled = 0; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
+  a.src = *src; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
   a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
   for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
     a.out_base[i] = dx; a.out_image_stride[i] = (long long)graphs->C_uni * hw; a.out_channels[i] = graphs->C_uni;
@@ -800,7 +798,7 @@ extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t*
   }
 
   Args a;
-  a.src = *src; a.src_scaled = 0; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
+  a.src = *src; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
   a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
   for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
     const bool on = i < src->n_datasets;

@@ -33,6 +33,10 @@ constexpr int kStageBytes = kStageFloats * 4;   // 2304
 constexpr int kStgW = 176;                      // staged label columns: <= 15 alignment + 32 cells x 5
 constexpr int kMaxR = 5;
 constexpr int kSpan = 160;
+#ifndef MDSEG_FWD_POLY_ROWS
+#define MDSEG_FWD_POLY_ROWS 0
+#endif
+constexpr int kPolyRows = MDSEG_FWD_POLY_ROWS;  // label rows of a cell whose exponentials run on the FMA pipe (ex2_fma2)
 
 struct Args {
   mdseg_src_table src;
@@ -140,16 +144,15 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     const int cc = (un.C - c_lo) < kKC ? (un.C - c_lo) : kKC;
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
+    uint32_t c2 = class_pair(c_lo);
 #pragma unroll 1
-    for (int c = 0; c < cc; ++c) {
+    for (int c = 0; c < cc; ++c, c2 = next_class2(c2)) {
       // corners, in log2 units, minus the corner's channel maximum: every interpolated exponent is <= 0
       const float v00 = fmaf(Sp[0], kLog2e, -c00), v01 = fmaf(Sp[1], kLog2e, -c01);
       const float v10 = fmaf(Sp[kBoxW], kLog2e, -c10), v11 = fmaf(Sp[kBoxW + 1], kLog2e, -c11);
       Sp += 2 * kBoxW;
       const float dv0 = v01 - v00, dv1 = v11 - v10;
       const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
-      const uint32_t ch = (uint32_t)__half_as_ushort(__int2half_rn(c_lo + c));
-      const uint32_t c2 = ch | (ch << 16);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const float2 h0 = fma2(L1W[p], DV0, V0);
@@ -158,7 +161,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
         for (int j = 0; j < RT; ++j) {
           const float2 arg = fma2(L1H[j], dd, h0);
           pick_label2(T[j][p], arg, LH[j][p], c2);
-          S[j][p] = add2(S[j][p], ex2_2(arg));
+          S[j][p] = add2(S[j][p], j < kPolyRows ? ex2_fma2(arg) : ex2_2(arg));
         }
       }
       if (NX5) {

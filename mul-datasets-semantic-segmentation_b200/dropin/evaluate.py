@@ -168,3 +168,63 @@ class MscEvalV0_AutoLink:
         ops.check_errors(dev)
         eye = torch.eye(n_classes, device=dev)
         return [torch.argmax(eye if h is None else h, dim=1) for h in hists]
+
+
+def target_bipart_from_hist(hist, bipart_graph, ignore_index=255):
+    """The bucket rules of evaluate.py:1886-1925, vectorised on the device.  Every unified class (column) belongs to
+    the dataset class with the largest graph weight (columns whose weights are all zero are skipped); within the
+    bucket of class k a column u becomes 0 when it holds < 10 % of the bucket's pixels or class k is < 10 % of the
+    pixels predicted as u, 1 when it holds > 50 % of the bucket, and stays `ignore_index` otherwise (also when the
+    bucket saw no pixel).  `hist` is the [n_cats, C_uni] label x unified-prediction histogram."""
+    h = hist.to(torch.float32)  # the reference accumulates in a float32 tensor (:1815)
+    max_value, max_index = torch.max(bipart_graph, dim=0)
+    cols = torch.arange(h.shape[1], device=h.device)
+    valid = max_value != 0
+    own = h[max_index, cols]
+    total = torch.zeros(h.shape[0], dtype=torch.float32, device=h.device).index_add_(0, max_index[valid], own[valid])
+    tot = total[max_index]
+    rate, share = own / tot, own / h.sum(dim=0)
+    zero = (rate < 0.1) | (share < 0.1)
+    one = ~zero & (rate > 0.5)
+    live = valid & (tot != 0)
+    out = ignore_index * torch.ones_like(bipart_graph)
+    val = torch.where(zero, torch.zeros_like(own), torch.where(one, torch.ones_like(own), ignore_index * torch.ones_like(own)))
+    out[max_index[live], cols[live]] = val[live].to(out.dtype)
+    return out
+
+
+@torch.no_grad()
+def eval_find_use_and_unuse_label(configer, net, dls=None):
+    """evaluate.py:1788-1930 — per dataset the rectangular ``[n_cats, C_uni]`` histogram of the labels against the
+    arg-max of the UNIFIED logits (prototype einsum -> bilinear up-sampling -> soft-max -> arg-max), then the
+    bucket rules that produce ``target_bi_graph`` for the GNN stage.  The einsum is the reference's own library GEMM;
+    up-sampling + arg-max (soft-max is monotone, no [C_uni, H, W] tensor) and the histogram run in libmdseg_b200.so.
+    `dls` defaults to the reference's ``get_data_loader(configer, aux_mode='train', distributed=..., stage=2)``."""
+    org_aux = net.aux_mode
+    n_datasets = configer.get("n_datasets")
+    ignore_index = configer.get('loss', 'ignore_index')
+    net.aux_mode = 'train'
+    net.eval()
+    unify_prototype, bipart_graph = net.unify_prototype, net.bipartite_graphs
+    if dls is None:
+        from lib.get_dataloader import get_data_loader  # the reference's loaders
+        dls = get_data_loader(configer, aux_mode='train', distributed=dist.is_initialized(), stage=2)
+    total_cats = int(sum(configer.get("dataset" + str(i + 1), "n_cats") for i in range(n_datasets))
+                     * configer.get('GNN', 'unify_ratio'))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    target_bipart = []
+    for i in range(n_datasets):
+        n_classes = configer.get(f'dataset{i + 1}', 'n_cats')
+        hist = torch.zeros(n_classes, total_cats, dtype=torch.int64, device=dev)
+        for imgs, label in dls[i]:
+            label = label.squeeze(1).to(dev, non_blocking=True)
+            H, W = label.shape[-2:]
+            emb = net(imgs.to(dev), dataset=i)
+            logits = torch.einsum('bchw,nc->bnhw', emb['seg'], unify_prototype.to(dev))
+            for b in range(label.shape[0]):
+                pred = ops.eval_fused([(logits[b], False)], (H, W))[0]
+                ops.confusion(label[b], pred, n_classes, total_cats, ignore=255, hist=hist)
+        ops.check_errors(dev)
+        target_bipart.append(target_bipart_from_hist(hist, bipart_graph[i].to(dev), ignore_index))
+    net.aux_mode = org_aux
+    return ['single_scale'], [], target_bipart

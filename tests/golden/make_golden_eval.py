@@ -194,9 +194,116 @@ def main():
     for k, r in enumerate(res):
         out[f"autolink_argmax{k}"] = r.numpy().astype(np.int64)
 
+    golden_find_use_and_unuse(ev, out)
+
     path = os.path.join(OUT, "evaluator.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", {k: float(out[k]) for k in out if k.endswith("_miou")})
+
+
+
+
+# ---- eval_find_use_and_unuse_label (evaluate.py:1788-1930): [n_cats, C_uni] histograms -> target_bi_graph ----------
+class _ProtoNet:
+    """Stands in for the segmentation net: emits seeded embeddings; carries unify_prototype / bipartite_graphs."""
+
+    def __init__(self, g, n_cats, c_uni, dim):
+        self.aux_mode = 'eval'
+        self.g, self.dim = g, dim
+        self.unify_prototype = torch.randn(c_uni, dim, generator=g)
+        self.bipartite_graphs = []
+        for c in n_cats:  # 0/1 column-one-hot graphs with a few empty columns (max_value == 0 -> skipped, :1894)
+            idx = torch.randint(0, c, (c_uni,), generator=g)
+            m = torch.zeros(c, c_uni)
+            m[idx, torch.arange(c_uni)] = 1
+            m[:, torch.rand(c_uni, generator=g) < 0.1] = 0
+            self.bipartite_graphs.append(m)
+        self.calls = []
+
+    def eval(self):
+        return self
+
+    def __call__(self, im, dataset=None):
+        # embeddings correlated with the label through the image's first channel (set by the loader below)
+        N, _, H, W = im.shape
+        emb = torch.randn(N, self.dim, H // 4, W // 4, generator=self.g)
+        emb = emb + 2.0 * self.unify_prototype[im[:, 0, ::4, ::4].long().clamp(0, self.unify_prototype.shape[0] - 1)].permute(0, 3, 1, 2)
+        self.calls.append(emb)
+        return {'seg': emb}
+
+
+def golden_find_use_and_unuse(ev, out):
+    g = torch.Generator().manual_seed(20261021)
+    n_cats, c_uni, dim, H, W = [5, 7], 16, 8, 32, 48
+    net = _ProtoNet(g, n_cats, c_uni, dim)
+    dls = []
+    for i, c in enumerate(n_cats):
+        dl = []
+        for _ in range(2):
+            coarse = torch.randint(0, c, (2, 1, H // 8, W // 8), generator=g).float()
+            lb = F.interpolate(coarse, size=(H, W), mode="nearest").long()
+            lb[torch.rand(2, 1, H, W, generator=g) < 0.08] = 255
+            # the "image" carries, in channel 0, a unified class the label's class maps to most of the time
+            cols = [torch.nonzero(net.bipartite_graphs[i][k]).flatten() for k in range(c)]
+            im = torch.zeros(2, 3, H, W)
+            lab0 = lb.squeeze(1).clone()
+            lab0[lab0 == 255] = 0
+            pick = torch.zeros_like(lab0)
+            for k in range(c):
+                if len(cols[k]):
+                    sel = lab0 == k
+                    choice = cols[k][torch.randint(0, len(cols[k]), (int(sel.sum()),), generator=g)]
+                    # skew: the first column of a class gets ~70 % of its pixels
+                    first = torch.rand(int(sel.sum()), generator=g) < 0.7
+                    choice[first] = cols[k][0]
+                    pick[sel] = choice
+            im[:, 0] = pick.float()
+            dl.append((im, lb))
+        dls.append(dl)
+
+    class Cfg:
+        def get(self, *k):
+            if k == ("n_datasets",):
+                return len(n_cats)
+            if k == ("loss", "ignore_index"):
+                return 255
+            if k == ("GNN", "unify_ratio"):
+                return c_uni / float(sum(n_cats)) + 1e-9
+            if len(k) == 2 and k[1] == "n_cats":
+                return n_cats[int(k[0][len("dataset"):]) - 1]
+            raise KeyError(k)
+
+    ev.get_data_loader = lambda *a, **k: dls
+    hists = []
+    real_bincount = np.bincount
+
+    def spy(x, *a, **k):
+        r = real_bincount(x, *a, **k)
+        hists.append(r.copy())
+        return r
+
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    np.bincount = spy
+    try:
+        heads, mious, target = ev.eval_find_use_and_unuse_label(Cfg(), net)
+    finally:
+        np.bincount = real_bincount
+        torch.Tensor.cuda = real_cuda
+    out["fuu_n_cats"] = np.array(n_cats)
+    out["fuu_c_uni"] = np.int64(c_uni)
+    out["fuu_proto"] = net.unify_prototype.numpy()
+    k = 0
+    for i, c in enumerate(n_cats):
+        out[f"fuu_graph{i}"] = net.bipartite_graphs[i].numpy()
+        out[f"fuu_target{i}"] = target[i].numpy()
+        for b, (_, lb) in enumerate(dls[i]):
+            out[f"fuu_label{i}_{b}"] = lb.numpy().astype(np.uint8)
+            out[f"fuu_emb{i}_{b}"] = net.calls[k].numpy()
+            out[f"fuu_hist{i}_{b}"] = hists[k].astype(np.int64)
+            k += 1
+    assert k == len(hists) == len(net.calls)
+    print("find_use_and_unuse:", [(int((t == 0).sum()), int((t == 1).sum()), int((t == 255).sum())) for t in target])
 
 
 if __name__ == "__main__":

@@ -289,3 +289,17 @@ def test_advgnn_gnn_stage_golden(golden):
         want = z[f"dgraph{i}"]
         got = graphs[i].grad.numpy() if graphs[i].grad is not None else np.zeros_like(want)
         assert np.abs(got - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30), i
+
+
+def test_find_use_and_unuse_hist_against_real_evaluate_py(golden):
+    """evaluate.py:1846-1866: prototype einsum -> upsample -> softmax -> argmax over C_uni -> [n_cats, C_uni] bincount."""
+    z = golden("evaluator.npz")
+    proto = torch.from_numpy(z["fuu_proto"])
+    c_uni = int(z["fuu_c_uni"])
+    for i, c in enumerate(z["fuu_n_cats"]):
+        for b in range(2):
+            lab = z[f"fuu_label{i}_{b}"].astype(np.int64).squeeze(1)
+            logits = tr.project(torch.from_numpy(z[f"fuu_emb{i}_{b}"]), proto)
+            pred = tr.eval_preds(tr.eval_probs([logits], lab.shape[-2:]))
+            h = ls.confusion(lab, pred.numpy(), int(c), c_uni)
+            assert np.array_equal(h.reshape(-1), z[f"fuu_hist{i}_{b}"])
