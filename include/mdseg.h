@@ -427,6 +427,31 @@ int mdseg_argmax_hist(const float* probs, int C, int64_t n_px, int64_t* pred,
 int mdseg_label_nearest(const void* in, int dtype, int Hin, int Win, void* out,
                         int Hout, int Wout, int n_images, void* stream);
 
+/*
+ * Label branch of the training data pipeline as ONE gather.  Replaces, per sample and on a
+ * DataLoader worker in the reference:  label = lb_map[label] (lib/base_dataset.py:81-82) ->
+ * cv2.resize(lb, (im_w, im_h), INTER_NEAREST) (lib/transform_cv2.py:43) -> np.pad(..., 255) (:52-53) ->
+ * crop (:57-61) -> horizontal flip (:71-77) -> int64 tensor (:300).
+ * One view per output image, in DEVICE memory (array of n_images structs); the host fills in the integers the
+ * reference's random draws produce.  Output pixels that fall into the padding get `pad_value` (255), which is NOT
+ * passed through the LUT (the reference pads after the LUT).  Source index rule of OpenCV's INTER_NEAREST:
+ * s = min(floor(d * (1. / ((double)dst / src))), src - 1).
+ */
+typedef struct mdseg_label_view {
+  const uint8_t* src;       /* raw label image, uint8 [src_h, src_w], device memory */
+  long long src_row_stride; /* bytes between source rows */
+  int src_h, src_w;
+  int im_h, im_w;           /* size after the resize */
+  int pad_top, pad_left;    /* rows / columns of padding in front of the resized image */
+  int crop_y, crop_x;       /* crop origin inside the padded image */
+  int flip;                 /* != 0: columns reversed after the crop */
+  int lut;                  /* row of `luts` applied to the source bytes; < 0: identity */
+} mdseg_label_view;
+
+/* out: [n_images, out_h, out_w] uint8 or int64; out_w % 16 == 0.  luts: [n_luts][256] uint8 or NULL. */
+int mdseg_label_pipeline(const mdseg_label_view* views /*device*/, int n_images, const uint8_t* luts, int n_luts,
+                         void* out, int out_dtype, int out_h, int out_w, int pad_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

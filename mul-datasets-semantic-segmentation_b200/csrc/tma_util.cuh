@@ -92,26 +92,6 @@ __device__ __forceinline__ uint32_t next_class2(uint32_t c2) {
 }
 __device__ __forceinline__ float2 ex2_2(float2 a) { return make_float2(ex2_approx(a.x), ex2_approx(a.y)); }
 
-// 2^x for two values on the FMA pipe instead of the XU pipe (MUFU.EX2 runs at 16 lanes/clk/SM and is the binding
-// unit of the forward kernel): round-to-nearest split x = n + f by the 1.5*2^23 trick, degree-5 minimax polynomial
-// for 2^f on [-0.5, 0.5] (max relative error 2.3e-7, the same as ex2.approx's 2 ulp), exponent patched in with one
-// integer multiply-add.  Arguments are clamped to >= -125 (the result is then < 2^-124: it vanishes in any sum whose
-// largest term is 1); NaN arguments do not stay NaN — callers keep at least one MUFU row per cell for that.
-__device__ __forceinline__ float2 ex2_fma2(float2 x) {
-  asm("max.f32 %0, %0, 0fC2FA0000;" : "+f"(x.x));
-  asm("max.f32 %0, %0, 0fC2FA0000;" : "+f"(x.y));
-  const float2 magic = make_float2(12582912.f, 12582912.f);
-  const float2 t = add2(x, magic);
-  const float2 f = sub2(x, sub2(t, magic));
-  float2 p = fma2(make_float2(0.0013276470126584172f, 0.0013276470126584172f), f,
-                  make_float2(0.009675540961325169f, 0.009675540961325169f));
-  p = fma2(p, f, make_float2(0.05550713464617729f, 0.05550713464617729f));
-  p = fma2(p, f, make_float2(0.24022120237350464f, 0.24022120237350464f));
-  p = fma2(p, f, make_float2(0.6931469440460205f, 0.6931469440460205f));
-  p = fma2(p, f, make_float2(1.0000001192092896f, 1.0000001192092896f));
-  return make_float2(__int_as_float(__float_as_int(t.x) * 0x800000 + __float_as_int(p.x)),
-                     __int_as_float(__float_as_int(t.y) * 0x800000 + __float_as_int(p.y)));
-}
 
 // align_corners=True source position of destination index `dst` expressed as (cell, lambda) with
 // cell in [0, n_in-2]: the last source index is folded into the last cell with lambda = 1, which

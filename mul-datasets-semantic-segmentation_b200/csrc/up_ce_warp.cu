@@ -33,10 +33,6 @@ constexpr int kStageBytes = kStageFloats * 4;   // 2304
 constexpr int kStgW = 176;                      // staged label columns: <= 15 alignment + 32 cells x 5
 constexpr int kMaxR = 5;
 constexpr int kSpan = 160;
-#ifndef MDSEG_FWD_POLY_ROWS
-#define MDSEG_FWD_POLY_ROWS 0
-#endif
-constexpr int kPolyRows = MDSEG_FWD_POLY_ROWS;  // label rows of a cell whose exponentials run on the FMA pipe (ex2_fma2)
 
 struct Args {
   mdseg_src_table src;
@@ -161,7 +157,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
         for (int j = 0; j < RT; ++j) {
           const float2 arg = fma2(L1H[j], dd, h0);
           pick_label2(T[j][p], arg, LH[j][p], c2);
-          S[j][p] = add2(S[j][p], j < kPolyRows ? ex2_fma2(arg) : ex2_2(arg));
+          S[j][p] = add2(S[j][p], ex2_2(arg));
         }
       }
       if (NX5) {

@@ -65,6 +65,12 @@ class EvalPasses(C.Structure):
     _fields_ = [("p", EvalPass * MAX_EVAL_PASSES), ("n_passes", C.c_int), ("dtype", C.c_int)]
 
 
+class LabelView(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_row_stride", C.c_longlong), ("src_h", C.c_int), ("src_w", C.c_int),
+                ("im_h", C.c_int), ("im_w", C.c_int), ("pad_top", C.c_int), ("pad_left", C.c_int),
+                ("crop_y", C.c_int), ("crop_x", C.c_int), ("flip", C.c_int), ("lut", C.c_int)]
+
+
 class GraphTable(C.Structure):
     _fields_ = [("g", SparseGraph * MAX_DATASETS), ("n_datasets", C.c_int), ("C_uni", C.c_int)]
 
@@ -115,6 +121,7 @@ SIGNATURES = {
     "mdseg_eval_fused": (_I, [C.POINTER(EvalPasses), _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, C.c_size_t, _P, _P]),
     "mdseg_argmax_hist": (_I, [_P, _I, _L, _P, _P, _I, _P, _P, _I, _P, _P]),
     "mdseg_label_nearest": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "mdseg_label_pipeline": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
 }
 
 

@@ -823,6 +823,46 @@ def label_nearest(label, size):
     return out
 
 
+# ---- f3: label branch of the data pipeline (LUT -> nearest resize -> pad -> crop -> flip) in one gather ----------
+def label_pipeline(srcs, plans, out_size, luts=None, lut_ids=None, out_dtype=torch.int64, pad_value=255):
+    """out[b] = flip(crop(pad(cv2_nearest_resize(lut[srcs[b]])))) for a batch of raw uint8 label images
+    (lib/base_dataset.py:81-82 + lib/transform_cv2.py:43-61,71-77,300) without materialising any intermediate.
+
+    srcs: list of uint8 CUDA tensors [H_b, W_b] (any row stride); plans: one dict per image with the integers
+    ``im_h, im_w, pad_top, pad_left, crop_y, crop_x, flip`` (see dropin.label_transform.plan_random_resized_crop);
+    out_size = (crop_h, crop_w), crop_w % 16 == 0; luts: uint8 [n_luts, 256] (or None), lut_ids[b] selects the row
+    (-1 / None: identity).  Returns [B, crop_h, crop_w] of `out_dtype` (torch.int64 like the reference, or uint8)."""
+    import numpy as np
+    _require_cuda(*srcs)
+    if len(srcs) != len(plans) or not srcs:
+        raise ValueError("label_pipeline: one plan per source image")
+    dev = srcs[0].device
+    views = (N.LabelView * len(srcs))()
+    for b, (t, pl) in enumerate(zip(srcs, plans)):
+        if t.dtype != torch.uint8 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError("label_pipeline: sources must be uint8 [H, W] with unit column stride")
+        v = views[b]
+        v.src, v.src_row_stride, v.src_h, v.src_w = t.data_ptr(), t.stride(0), t.shape[0], t.shape[1]
+        v.im_h, v.im_w = int(pl["im_h"]), int(pl["im_w"])
+        v.pad_top, v.pad_left = int(pl.get("pad_top", 0)), int(pl.get("pad_left", 0))
+        v.crop_y, v.crop_x, v.flip = int(pl.get("crop_y", 0)), int(pl.get("crop_x", 0)), int(bool(pl.get("flip", False)))
+        v.lut = int(lut_ids[b]) if lut_ids is not None else (0 if luts is not None else -1)
+        if v.im_h <= 0 or v.im_w <= 0:
+            raise ValueError("label_pipeline: empty resized image")
+    table = torch.from_numpy(np.frombuffer(bytes(views), dtype=np.uint8).copy()).to(dev, non_blocking=True)
+    n_luts = 0
+    if luts is not None:
+        luts = torch.as_tensor(luts).to(device=dev, dtype=torch.uint8).reshape(-1, 256).contiguous()
+        n_luts = luts.shape[0]
+    Ho, Wo = int(out_size[0]), int(out_size[1])
+    if out_dtype not in (torch.int64, torch.uint8):
+        raise TypeError("label_pipeline: out_dtype must be torch.int64 or torch.uint8")
+    out = torch.empty(len(srcs), Ho, Wo, dtype=out_dtype, device=dev)
+    N.call("mdseg_label_pipeline", _ptr(table), len(srcs), _ptr(luts), n_luts, _ptr(out), _DT[out_dtype], Ho, Wo,
+           int(pad_value), _stream())
+    return out
+
+
 def neg_log(p):
     """-log(p) in fp32, as torch computes OhemCELoss.thresh (ohem_ce_loss.py:17)."""
     return float(-torch.log(torch.tensor(p, dtype=torch.float)))

@@ -193,3 +193,55 @@ def batch_layout(labels_per_dataset):
     lb = np.concatenate(labels_per_dataset, axis=0)
     ids = np.concatenate([np.full(len(l), j, dtype=np.int32) for j, l in enumerate(labels_per_dataset)])
     return lb, ids
+
+
+# ---- label branch of the training transforms (lib/transform_cv2.py) ---------------------------------------------
+def cv2_nearest_resize(label, size):
+    """cv2.resize(lb, (im_w, im_h), interpolation=cv2.INTER_NEAREST) (lib/transform_cv2.py:43).  Third-party
+    arithmetic (opencv-python, 4.13.0 in the build container; the reference pins none): restated from OpenCV 4.x
+    imgproc/resize.cpp — resize() sets inv_scale = (double)dsize / ssize and scale = 1. / inv_scale, resizeNN() takes
+    src = min(cvFloor(dst * scale), ssize - 1) on both axes.  Pinned bit-exact against the real cv2 through
+    tests/golden/label_pipeline.npz (tests/golden/make_golden_label_pipeline.py)."""
+    label = np.asarray(label)
+    Hs, Ws = label.shape[:2]
+    im_h, im_w = size
+    ify = 1.0 / (float(im_h) / float(Hs))
+    ifx = 1.0 / (float(im_w) / float(Ws))
+    ys = np.minimum(np.floor(np.arange(im_h, dtype=np.float64) * ify).astype(np.int64), Hs - 1)
+    xs = np.minimum(np.floor(np.arange(im_w, dtype=np.float64) * ifx).astype(np.int64), Ws - 1)
+    return label[ys[:, None], xs[None, :]]
+
+
+def plan_random_resized_crop(shape, scales, size, rng=np.random):
+    """The integers RandomResizedCrop.__call__ derives from its random draws (lib/transform_cv2.py:22-62), drawing
+    from `rng` in the same order: uniform(min, max) for the scale, then random(2) for the crop origin."""
+    H, W = shape
+    crop_h, crop_w = size
+    scale = rng.uniform(min(scales), max(scales))
+    if np.min([H, W]) < 1080:
+        scale = scale * (1080 / np.min([H, W]))
+    im_h, im_w = [int(np.ceil(el * scale)) for el in (H, W)]
+    if (im_h, im_w) == (crop_h, crop_w):
+        return dict(im_h=im_h, im_w=im_w, pad_top=0, pad_left=0, crop_y=0, crop_x=0)
+    pad_h = (crop_h - im_h) // 2 + 1 if im_h < crop_h else 0
+    pad_w = (crop_w - im_w) // 2 + 1 if im_w < crop_w else 0
+    sh, sw = rng.random(2)
+    sh, sw = int(sh * (im_h + 2 * pad_h - crop_h)), int(sw * (im_w + 2 * pad_w - crop_w))
+    return dict(im_h=im_h, im_w=im_w, pad_top=pad_h, pad_left=pad_w, crop_y=sh, crop_x=sw)
+
+
+def label_transform_chain(label, lb_map, plan, size):
+    """lb_map gather (lib/base_dataset.py:81-82) -> RandomResizedCrop's label branch (lib/transform_cv2.py:43-61) ->
+    RandomHorizontalFlip (:71-77) -> int64 (:300), step by step with numpy as the reference does."""
+    lb = np.asarray(label)
+    if lb_map is not None:
+        lb = np.asarray(lb_map)[lb]
+    lb = cv2_nearest_resize(lb, (plan["im_h"], plan["im_w"]))
+    ph, pw = plan.get("pad_top", 0), plan.get("pad_left", 0)
+    if ph > 0 or pw > 0:
+        lb = np.pad(lb, ((ph, ph), (pw, pw)), 'constant', constant_values=IGNORE)
+    sh, sw = plan.get("crop_y", 0), plan.get("crop_x", 0)
+    lb = lb[sh:sh + size[0], sw:sw + size[1]]
+    if plan.get("flip", False):
+        lb = lb[:, ::-1]
+    return lb.astype(np.int64)

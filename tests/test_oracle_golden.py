@@ -303,3 +303,28 @@ def test_find_use_and_unuse_hist_against_real_evaluate_py(golden):
             pred = tr.eval_preds(tr.eval_probs([logits], lab.shape[-2:]))
             h = ls.confusion(lab, pred.numpy(), int(c), c_uni)
             assert np.array_equal(h.reshape(-1), z[f"fuu_hist{i}_{b}"])
+
+
+# ---- label branch of the data pipeline, pinned on the real lib/transform_cv2.py + cv2 ---------------------------
+def _label_pipeline_cases(z):
+    for tag in ("crop", "pad", "wide"):
+        n = int(z[f"{tag}_n"])
+        yield (tag, int(z[f"{tag}_seed"]), tuple(float(v) for v in z[f"{tag}_scales"]),
+               tuple(int(v) for v in z[f"{tag}_size"]), z[f"{tag}_lut"],
+               [z[f"{tag}_raw{k}"] for k in range(n)], [z[f"{tag}_lb{k}"] for k in range(n)])
+
+
+def test_label_transform_chain_against_real_transform_cv2(golden):
+    """oracle.label_space.{plan_random_resized_crop, cv2_nearest_resize, label_transform_chain} against the output of
+    RandomResizedCrop -> RandomHorizontalFlip -> ColorJitter -> ToTensor of the reference (real cv2.resize), several
+    samples from one seeded np.random stream (tests/golden/make_golden_label_pipeline.py)."""
+    z = golden("label_pipeline.npz")
+    for tag, seed, scales, size, lut, raws, wants in _label_pipeline_cases(z):
+        rng = np.random.RandomState(seed)  # np.random.seed(seed) seeds the same legacy generator
+        for raw, want in zip(raws, wants):
+            plan = ls.plan_random_resized_crop(raw.shape, scales, size, rng)
+            plan["flip"] = not (rng.random() < 0.5)
+            for _ in range(3):
+                rng.uniform(0.0, 1.0)  # ColorJitter's three draws
+            got = ls.label_transform_chain(raw, lut, plan, size)
+            assert got.dtype == np.int64 and np.array_equal(got, want.astype(np.int64)), tag
