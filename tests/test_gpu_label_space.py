@@ -238,3 +238,20 @@ def test_batched_ops_flag_bad_dataset_id(ops):
     assert int(out[1].min()) == 255 and int(out[0].max()) == 0
     with pytest.raises(RuntimeError, match="dataset id"):
         ops.check_errors(DEV)
+
+
+def test_lb_map_gather_against_real_dataset_readers(ops, golden):
+    """a1 pinned: the lb_map LUTs of the seven REAL reader classes (CityScapes, Mapi, Sunrgbd, Bdd100k, Idd, ade2016,
+    Coco_data) and their __getitem__ label output (tests/golden/make_golden_lb_maps.py), one image at a time and as a
+    mixed-dataset batch in one launch."""
+    z = golden("lb_maps.npz")
+    raw = torch.from_numpy(z["raw"]).to(DEV)
+    for i in range(7):
+        for out_dt in (torch.uint8, torch.int64):  # int64: what ToTensor makes of it (lib/transform_cv2.py:300)
+            out = ops.lut_remap(raw, z[f"lb_map{i}"], out_dtype=out_dt)
+            assert np.array_equal(out.cpu().numpy().astype(np.uint8), z[f"label{i}"]), str(z["names"][i])
+    ids = [6, 0, 3, 3, 5, 1, 2, 4]
+    luts = np.stack([z[f"lb_map{i}"] for i in range(7)])
+    out = ops.lut_remap_images(raw.unsqueeze(0).repeat(len(ids), 1, 1), luts, ids)
+    for b, i in enumerate(ids):
+        assert np.array_equal(out[b].cpu().numpy(), z[f"label{i}"]), b

@@ -328,3 +328,13 @@ def test_label_transform_chain_against_real_transform_cv2(golden):
                 rng.uniform(0.0, 1.0)  # ColorJitter's three draws
             got = ls.label_transform_chain(raw, lut, plan, size)
             assert got.dtype == np.int64 and np.array_equal(got, want.astype(np.int64)), tag
+
+
+def test_lb_map_gather_against_real_dataset_readers(golden):
+    """lib/base_dataset.py:81-82 through the REAL reader classes of the seven ltbgnn_7_datasets_snp datasets
+    (tests/golden/make_golden_lb_maps.py): oracle.label_space.lut_gather reproduces their __getitem__ label."""
+    z = golden("lb_maps.npz")
+    for i in range(7):
+        lut = z[f"lb_map{i}"]
+        assert lut.shape == (256,) and lut.dtype == np.uint8
+        assert np.array_equal(ls.lut_gather(z["raw"], lut), z[f"label{i}"]), str(z["names"][i])
