@@ -38,11 +38,39 @@ constexpr int kStages = 2;
 constexpr int kStageFloats = kKC * 2 * kBoxW;   // 1152
 constexpr int kStageBytes = kStageFloats * 4;   // 4608
 constexpr int kCG = 16;                         // classes per unit
-constexpr int kOwn = 28;                        // owned columns per strip: 7 aligned groups of four (16-byte stores)
-constexpr int kStgW = 160;                      // staged label columns: <= 15 alignment + 29 cells x 5
+constexpr int kOwn28 = 28;                      // one-warp CTAs: owned columns per strip, 7 aligned groups of four (16-byte stores)
+constexpr int kOwn = kOwn28;
+constexpr int kStgW28 = 160;                    // one-warp CTAs: staged label columns, <= 15 alignment + 29 cells x 5
 constexpr int kMaxR = 5;
 constexpr int kEnt = 384;                       // (class, output channel) pairs of one class group cached in shared memory
 constexpr uint32_t kNoEnt = 0xffffffffu;
+
+// Shared-memory carve-up of ONE warp.  ROW = false: a CTA is one warp owning 28 columns (lane 0 recomputes the halo cell
+// of the strip on its left).  ROW = true: a CTA is the w / 32 warps of a whole low-res row, every lane owns a cell AND a
+// column, and the right-column sums of lane 31 travel to lane 0 of the next warp through `xchg` (two slots of
+// [kKC classes][upper, lower], guarded by a full / empty mbarrier pair each, in the producer's region).
+template <bool ROW>
+struct Lay {
+  static constexpr int kOwn = ROW ? 32 : kOwn28;
+  static constexpr int kStgW = ROW ? 176 : kStgW28;  // ROW: <= 15 alignment + 32 cells x 5
+  static constexpr size_t kOffCarry = (size_t)kStages * kStageBytes;
+  static constexpr size_t kOffLw = kOffCarry + (size_t)kCG * 32 * 4;
+  static constexpr size_t kOffLab = kOffLw + (size_t)kMaxR * kStgW * 4;
+  static constexpr size_t kOffEnt = kOffLab + (size_t)kMaxR * kStgW;
+  static constexpr size_t kOffTile = kOffEnt + (size_t)kEnt * 4;
+  static constexpr size_t kOffEptr = kOffTile + (size_t)kKC * kOwn * 4;
+  static constexpr size_t kOffBars = kOffEptr + 16;
+  static constexpr size_t kOffXbar = kOffBars + (kStages + 1) * 8;        // ROW: full[2], empty[2]
+  static constexpr size_t kOffXchg = kOffXbar + 4 * 8;                    // ROW: [2 slots][kKC][2] floats
+  static constexpr size_t kSmem = ROW ? ((kOffXchg + 2 * kKC * 2 * 4 + 127) / 128) * 128 : kOffXbar;
+  static_assert(kCG / kKC + 1 <= 4, "eptr holds one quad offset per chunk of a class group, plus the end");
+  static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffEnt % 16 == 0 && kOffTile % 16 == 0 && kOffBars % 8 == 0,
+                "shared memory carve-up alignment");
+};
+static_assert(Lay<false>::kSmem <= 13568, "16 resident one-warp CTAs per SM need <= 13568 bytes of shared memory each");
+static_assert(16 * Lay<true>::kSmem <= 232448, "a 16-warp row CTA must fit the 227 KB of one SM");
+constexpr size_t kSmem = Lay<false>::kSmem;
+constexpr int kMaxRowWarps = 16;
 
 struct GraphDev {
   const int* csr_ptr;  // NULL: identity (output channel = class)
@@ -163,7 +191,7 @@ __device__ __forceinline__ void store4(__half* p, const float4 v) {
 // Finished rows of one chunk of classes (tile[class in chunk][column in strip]) -> every output channel of
 // those classes.  ents[4q + o] = channel | class-in-chunk << 16 (kNoEnt pads a chunk to whole quads); lane
 // octet o takes entry 4q + o, lane t of the octet the columns 4t .. 4t+3 of the strip.
-template <typename TO>
+template <typename TO, int OWN>
 __device__ __forceinline__ void broadcast_chunk(const Unit& un, TO* orow, const uint32_t* ents, int q0, int q1,
                                                 const float* tile, int hw) {
   const int o = un.lane >> 3, t = un.lane & 7;
@@ -174,7 +202,7 @@ __device__ __forceinline__ void broadcast_chunk(const Unit& un, TO* orow, const 
   for (int q = q0; q < q1; ++q) {
     const uint32_t e = ents[4 * q + o];
     if (col_ok && e != kNoEnt) {
-      const float4 v = *reinterpret_cast<const float4*>(tile + (e >> 16) * kOwn + 4 * t);
+      const float4 v = *reinterpret_cast<const float4*>(tile + (e >> 16) * OWN + 4 * t);
       store4(base + (int64_t)((e & 0xffffu) * (uint32_t)hw), v);
     }
   }
@@ -200,23 +228,28 @@ __device__ __forceinline__ void store_class(const Args& a, const GraphDev& gd, c
 }
 
 // lane 0: queue the selection state (lw2 + class byte rows) of cell-row g into shared memory
+template <int STGW>
 __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int Ys, int R, float* lw2s, uint8_t* labs,
                                               uint64_t* sbar) {
   mbar_expect_tx(sbar, (uint32_t)(R * un.wst * 5));
   for (int j = 0; j < R; ++j) {
     const int64_t p = ((int64_t)un.b * a.gm.H + (Ys + j)) * a.gm.W + un.Xa;
-    bulk_g2s(lw2s + j * kStgW, a.lw2 + p, (uint32_t)(un.wst * 4), sbar);
-    bulk_g2s(labs + j * kStgW, a.sel8 + p, (uint32_t)un.wst, sbar);
+    bulk_g2s(lw2s + j * STGW, a.lw2 + p, (uint32_t)(un.wst * 4), sbar);
+    bulk_g2s(labs + j * STGW, a.sel8 + p, (uint32_t)un.wst, sbar);
   }
 }
 
 // One cell-row: all class chunks of the unit.  RT rows / 4 (+1 when NX5) columns are the compiled loop bounds.
-template <typename TO, int RT, bool NX5>
+// ROW: `xmine` / `xbar_mine` are this warp's exchange slots and their full[2] / empty[2] barriers (it is the producer for
+// the warp on its right), `xleft` / `xbar_left` those of the warp on its left (NULL for the first warp of the row).
+template <typename TO, int RT, bool NX5, bool ROW>
 __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, const GraphDev& gd, const Unit& un,
                                          TO* outb, int g, int R, int Ys_next, int R_next, const float (&l1w)[5],
                                          const float (&l1h)[kMaxR],
                                          float* stages, uint64_t* bars, float* carry, float* lw2s,
-                                         uint8_t* labs, const uint32_t* ents, const int* eptr, float* tile) {
+                                         uint8_t* labs, const uint32_t* ents, const int* eptr, float* tile,
+                                         float* xmine, uint64_t* xbar_mine, const float* xleft, uint64_t* xbar_left) {
+  constexpr int kOwn = Lay<ROW>::kOwn, kStgW = Lay<ROW>::kStgW;
   const int lane = un.lane;
   const float kInf = __int_as_float(0x7f800000);
   // per-pixel exponent offsets and class bytes of this lane's cell, from the staged rows
@@ -245,7 +278,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     lh4[j] = hv[4] | (0x5bf8u << 16);  // high half 255.0: never a class
   }
   __syncwarp();
-  if (lane == 0 && g + 1 < un.g1) issue_staging(a, un, Ys_next, R_next, lw2s, labs, &bars[kStages]);
+  if (lane == 0 && g + 1 < un.g1) issue_staging<kStgW>(a, un, Ys_next, R_next, lw2s, labs, &bars[kStages]);
 
   float2 L1H[RT];
 #pragma unroll
@@ -266,6 +299,8 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     const int cc = (un.c_end - c_lo) < kKC ? (un.c_end - c_lo) : kKC;
 
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
+    const int xs = q & 1;  // exchange slot of this chunk
+    if (ROW && xmine != nullptr && q >= 2) mbar_wait(&xbar_mine[2 + xs], (uint32_t)(((q >> 1) - 1) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
     // corners of the next class are fetched while the current one is being computed (the loop stays rolled)
     float n00 = Sp[0], n01 = Sp[1], n10 = Sp[kBoxW], n11 = Sp[kBoxW + 1];
@@ -318,7 +353,11 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       lr *= un.wsign;
       float gu = __shfl_up_sync(0xffffffffu, ur, 1);
       float gl = __shfl_up_sync(0xffffffffu, lr, 1);
-      if (lane == 0) { gu = 0.f; gl = 0.f; }
+      if (lane == 0) { gu = 0.f; gl = 0.f; }  // ROW: the left warp's part is added after the class loop
+      if (ROW && xmine != nullptr && lane == 31) {
+        xmine[(xs * kKC + c) * 2] = ur;
+        xmine[(xs * kKC + c) * 2 + 1] = lr;
+      }
       // vertical: add the lower-row half carried from the cell-row above; the finished row leaves the warp
       const int cg = k * kKC + c;
       const float up = uo + gu;
@@ -327,9 +366,30 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       if (first_partial) {
         if (un.own) a.scrA[(((int64_t)un.b * a.n_seg + un.seg) * a.c_scr + (c_lo + c)) * a.gm.w + un.x] = up;
       } else if (un.cached) {
-        if (lane >= 1 && lane <= kOwn) tile[c * kOwn + lane - 1] = rowv;
+        if (ROW) tile[c * kOwn + lane] = rowv;
+        else if (lane >= 1 && lane <= kOwn) tile[c * kOwn + lane - 1] = rowv;
       } else {
         store_class<TO>(a, gd, un, outb, cg, g, rowv);
+      }
+    }
+    if (ROW) {
+      if (xmine != nullptr && lane == 31) mbar_arrive(&xbar_mine[xs]);  // release: the slot is full
+      if (xleft != nullptr) {
+        // column x0 also receives the right-column sums of the last cell of the warp on the left: lane c adds those of
+        // class c to the finished row (or to the scratch half of a segment's first row) and to the carry
+        mbar_wait(&xbar_left[xs], (uint32_t)((q >> 1) & 1));
+        __syncwarp();
+        if (lane < cc) {
+          const float xu = xleft[(xs * kKC + lane) * 2], xl = xleft[(xs * kKC + lane) * 2 + 1];
+          if (first_partial) {
+            a.scrA[(((int64_t)un.b * a.n_seg + un.seg) * a.c_scr + (c_lo + lane)) * a.gm.w + un.x0] += xu;
+          } else {
+            tile[lane * kOwn] += xu;
+          }
+          carry[(k * kKC + lane) * 32] += xl;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xbar_left[2 + xs]);  // the slot may be refilled
       }
     }
     __syncwarp();
@@ -339,44 +399,43 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       load_4d(stages + slot * kStageFloats, map, &bars[slot], un.box_x, un.g0 + qn / un.n_ch,
               un.c_beg + (qn % un.n_ch) * kKC, un.b);
     }
-    if (un.cached && !first_partial) broadcast_chunk<TO>(un, orow, ents, eptr[k], eptr[k + 1], tile, a.gm.h * a.gm.w);
+    if (un.cached && !first_partial) broadcast_chunk<TO, kOwn>(un, orow, ents, eptr[k], eptr[k + 1], tile, a.gm.h * a.gm.w);
   }
 }
 
-constexpr size_t kOffCarry = (size_t)kStages * kStageBytes;
-constexpr size_t kOffLw = kOffCarry + (size_t)kCG * 32 * 4;
-constexpr size_t kOffLab = kOffLw + (size_t)kMaxR * kStgW * 4;
-constexpr size_t kOffEnt = kOffLab + (size_t)kMaxR * kStgW;
-constexpr size_t kOffTile = kOffEnt + (size_t)kEnt * 4;
-constexpr size_t kOffEptr = kOffTile + (size_t)kKC * kOwn * 4;
-constexpr size_t kOffBars = kOffEptr + 16;
-constexpr size_t kSmem = kOffBars + (kStages + 1) * 8;
-static_assert(kCG / kKC + 1 <= 4, "eptr holds one quad offset per chunk of a class group, plus the end");
-static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffEnt % 16 == 0 && kOffTile % 16 == 0 && kOffBars % 8 == 0,
-              "shared memory carve-up alignment");
-static_assert(kSmem <= 13568, "16 resident warps per SM need <= 13568 bytes of shared memory each");
-
-template <typename TO>
-__global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+template <typename TO, bool ROW>
+__global__ void __launch_bounds__(ROW ? 32 * kMaxRowWarps : 32, ROW ? 1 : 16)
+mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a) {
+  using L = Lay<ROW>;
+  constexpr int kOwn = L::kOwn, kStgW = L::kStgW;
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  const int wi = ROW ? (int)(threadIdx.x >> 5) : 0;           // warp of the row CTA = strip
+  const int n_w = ROW ? (int)(blockDim.x >> 5) : 1;
+  unsigned char* smem_raw = smem_all + (size_t)wi * L::kSmem;
   float* stages = reinterpret_cast<float*>(smem_raw);
-  float* carry = reinterpret_cast<float*>(smem_raw + kOffCarry); // [kCG][32]
-  float* lw2s = reinterpret_cast<float*>(smem_raw + kOffLw);     // [kMaxR][kStgW]
-  uint8_t* labs = smem_raw + kOffLab;                            // [kMaxR][kStgW]
-  uint32_t* ents = reinterpret_cast<uint32_t*>(smem_raw + kOffEnt);  // [kEnt] channel | class-in-chunk << 16
-  float* tile = reinterpret_cast<float*>(smem_raw + kOffTile);   // [kKC][kOwn] finished rows of one chunk
-  int* eptr = reinterpret_cast<int*>(smem_raw + kOffEptr);       // [n_ch + 1] first quad of every chunk
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);  // stage ring + staging barrier
+  float* carry = reinterpret_cast<float*>(smem_raw + L::kOffCarry); // [kCG][32]
+  float* lw2s = reinterpret_cast<float*>(smem_raw + L::kOffLw);     // [kMaxR][kStgW]
+  uint8_t* labs = smem_raw + L::kOffLab;                            // [kMaxR][kStgW]
+  uint32_t* ents = reinterpret_cast<uint32_t*>(smem_raw + L::kOffEnt);  // [kEnt] channel | class-in-chunk << 16
+  float* tile = reinterpret_cast<float*>(smem_raw + L::kOffTile);   // [kKC][kOwn] finished rows of one chunk
+  int* eptr = reinterpret_cast<int*>(smem_raw + L::kOffEptr);       // [n_ch + 1] first quad of every chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::kOffBars);  // stage ring + staging barrier
+  // ROW: exchange with the neighbouring warps (this warp produces for the one on its right)
+  const bool has_right = ROW && wi + 1 < n_w, has_left = ROW && wi > 0;
+  uint64_t* xbar_mine = has_right ? reinterpret_cast<uint64_t*>(smem_raw + L::kOffXbar) : nullptr;
+  float* xmine = has_right ? reinterpret_cast<float*>(smem_raw + L::kOffXchg) : nullptr;
+  uint64_t* xbar_left = has_left ? reinterpret_cast<uint64_t*>(smem_raw - L::kSmem + L::kOffXbar) : nullptr;
+  const float* xleft = has_left ? reinterpret_cast<const float*>(smem_raw - L::kSmem + L::kOffXchg) : nullptr;
 
   const Geom& gm = a.gm;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, grp = blockIdx.y;
-  const int strip = blockIdx.x % a.n_strips, seg = blockIdx.x / a.n_strips;
+  const int strip = ROW ? wi : (int)(blockIdx.x % a.n_strips), seg = ROW ? (int)blockIdx.x : (int)(blockIdx.x / a.n_strips);
   const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
   const int h = gm.h, w = gm.w;
   const int x0 = strip * kOwn;
-  const int x = x0 + lane - 1;
-  const bool own = lane >= 1 && lane <= kOwn && x <= w - 1;
+  const int x = ROW ? x0 + lane : x0 + lane - 1;  // ROW: lane l owns cell x0 + l and column x0 + l
+  const bool own = ROW ? x <= w - 1 : (lane >= 1 && lane <= kOwn && x <= w - 1);
   const int g0 = seg * a.seg_rows;
   const int g1 = (g0 + a.seg_rows < h - 1) ? g0 + a.seg_rows : h - 1;
   const bool last_seg = (g1 == h - 1);
@@ -399,7 +458,7 @@ __global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__
   const float wsel = (a.grad_out ? a.grad_out[a.src.seg_per_dataset ? d : 0] : 1.f) * a.grad_scale * st->inv_n_sel;
 
   // horizontal geometry of this lane's cell
-  const bool cell_ok = (x >= 0) && (x <= w - 2) && lane <= kOwn;
+  const bool cell_ok = (x >= 0) && (x <= w - 2) && (ROW || lane <= kOwn);
   int Xbeg = 0, Xend = 0;
   if (cell_ok) cell_span(gm.xm, x, gm.W, Xbeg, Xend);
   const int nx = Xend - Xbeg;
@@ -420,7 +479,7 @@ __global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__
   un.x0 = x0; un.ncols = (w - x0) < kOwn ? (w - x0) : kOwn;
   un.n_ch = (c_end - c_beg + kKC - 1) / kKC;
   un.g0 = g0; un.g1 = g1; un.own = own;
-  un.box_x = (x0 > 0 ? x0 - 1 : 0) & ~3;
+  un.box_x = ROW ? x0 : ((x0 > 0 ? x0 - 1 : 0) & ~3);
   un.xl = cell_ok ? x - un.box_x : 0;
   un.n_loads = (g1 - g0) * un.n_ch;
   un.Xa = Xw0 & ~15;
@@ -432,11 +491,13 @@ __global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__
   if (lane == 0) {
     prefetch_map(map);
     for (int s = 0; s <= kStages; ++s) mbar_init(&bars[s], 1);
+    if (has_right)
+      for (int s = 0; s < 4; ++s) mbar_init(&xbar_mine[s], 1);
     mbar_fence_init();
     {
       int Ys0, Ye0;
       cell_span(gm.ym, g0, gm.H, Ys0, Ye0);
-      issue_staging(a, un, Ys0, Ye0 - Ys0, lw2s, labs, &bars[kStages]);
+      issue_staging<kStgW>(a, un, Ys0, Ye0 - Ys0, lw2s, labs, &bars[kStages]);
     }
     for (int qn = 0; qn < kStages && qn < un.n_loads; ++qn) {
       mbar_expect_tx(&bars[qn], kStageBytes);
@@ -469,6 +530,7 @@ __global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__
     un.cached = pos <= kEnt;
   }
   __syncwarp();
+  if (ROW) __syncthreads();  // the neighbours' exchange barriers are initialised (every early exit above is CTA-uniform)
 
   // label-row range of every cell-row of the segment: lane t holds the first label row of cell-row g0 + t
   int ys_tab = gm.H;
@@ -486,8 +548,9 @@ __global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__
     }
     const int Rn = __shfl_sync(0xffffffffu, ys_tab, (g - g0 + 2) & 31) - Ye;  // rows of the next cell-row
     mbar_wait(&bars[kStages], (uint32_t)((g - g0) & 1));
-#define MDSEG_ROW(RT, N5) \
-  cell_row<TO, RT, N5>(a, map, gd, un, outb, g, R, Ye, Rn, l1w, l1h, stages, bars, carry, lw2s, labs, ents, eptr, tile)
+#define MDSEG_ROW(RT, N5)                                                                                           \
+  cell_row<TO, RT, N5, ROW>(a, map, gd, un, outb, g, R, Ye, Rn, l1w, l1h, stages, bars, carry, lw2s, labs, ents, eptr, \
+                            tile, xmine, xbar_mine, xleft, xbar_left)
     if (R <= 4) {
       if (nx5) MDSEG_ROW(4, true); else MDSEG_ROW(4, false);
     } else {
@@ -501,9 +564,10 @@ __global__ void __launch_bounds__(32, 16) mds_bwd_kernel(const __grid_constant__
     TO* olast = outb + (int64_t)(h - 1) * w + x0;
     for (int k = 0; k < un.n_ch; ++k) {
       for (int j = 0; j < kKC && k * kKC + j < c_end - c_beg; ++j)
-        if (lane >= 1 && lane <= kOwn) tile[j * kOwn + lane - 1] = carry[(k * kKC + j) * 32 + lane];
+        if (ROW) tile[j * kOwn + lane] = carry[(k * kKC + j) * 32 + lane];
+        else if (lane >= 1 && lane <= kOwn) tile[j * kOwn + lane - 1] = carry[(k * kKC + j) * 32 + lane];
       __syncwarp();
-      broadcast_chunk<TO>(un, olast, ents, eptr[k], eptr[k + 1], tile, h * w);
+      broadcast_chunk<TO, kOwn>(un, olast, ents, eptr[k], eptr[k + 1], tile, h * w);
     }
   } else {
     for (int cg = 0; cg < c_end - c_beg; ++cg) {
@@ -578,8 +642,15 @@ int launch_prep(const Args& a, int n_images, cudaStream_t s) {
   return 0;
 }
 
+// Row CTAs (one warp per 32 columns, no halo cells, no idle lanes) when the row is a whole number of warps that fit one
+// CTA and every class group's channel list fits the shared-memory cache (`ents_fit`: the uncached per-class stores
+// cannot take the neighbour's column-0 contribution).
+bool row_route(const Args& a, bool ents_fit) {
+  return ents_fit && a.gm.w % 32 == 0 && a.gm.w / 32 <= kMaxRowWarps;
+}
+
 template <typename TO>
-int launch(int label_dtype, const Maps& maps, const Args& a, int n_images, int max_c, cudaStream_t s) {
+int launch(int label_dtype, const Maps& maps, const Args& a, int n_images, int max_c, bool ents_fit, cudaStream_t s) {
   int rc = 2;
   switch (label_dtype) {
     case MDSEG_U8: rc = launch_prep<uint8_t>(a, n_images, s); break;
@@ -588,10 +659,19 @@ int launch(int label_dtype, const Maps& maps, const Args& a, int n_images, int m
     default: set_error("mdseg_mds_bwd: unsupported label dtype %d", label_dtype);
   }
   if (rc) return rc;
-  auto k = mds_bwd_kernel<TO>;
-  MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-  dim3 grid((unsigned)(a.n_strips * a.n_seg), (unsigned)((max_c + kCG - 1) / kCG), (unsigned)n_images);
-  k<<<grid, 32, kSmem, s>>>(maps, a);
+  if (row_route(a, ents_fit)) {
+    const int n_w = a.gm.w / 32;
+    const size_t smem = (size_t)n_w * Lay<true>::kSmem;
+    auto k = mds_bwd_kernel<TO, true>;
+    MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)a.n_seg, (unsigned)((max_c + kCG - 1) / kCG), (unsigned)n_images);
+    k<<<grid, 32 * n_w, smem, s>>>(maps, a);
+  } else {
+    auto k = mds_bwd_kernel<TO, false>;
+    MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    dim3 grid((unsigned)(a.n_strips * a.n_seg), (unsigned)((max_c + kCG - 1) / kCG), (unsigned)n_images);
+    k<<<grid, 32, kSmem, s>>>(maps, a);
+  }
   MDSEG_LAUNCH_OK();
   if (a.n_seg > 1) {
     dim3 g2((unsigned)(((int64_t)max_c * (a.gm.w / 4) + 255) / 256), (unsigned)(a.n_seg - 1), (unsigned)n_images);
@@ -714,10 +794,12 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
   a.sel8 = reinterpret_cast<uint8_t*>(a.lw2 + (size_t)n_images * H * W);
   tma::Maps maps;
   if (int rc = tma::make_maps(a.src, gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
+  bool ents_fit = true;  // a class group's (class, channel) pairs, each chunk padded to quads, within kEnt
+  for (int i = 0; i < src->n_datasets; ++i) ents_fit = ents_fit && graphs->g[i].nnz + 8 <= kEnt;
   switch (dx_dtype) {
-    case MDSEG_F32: return launch<float>(label_dtype, maps, a, n_images, c_max, s);
-    case MDSEG_BF16: return launch<__nv_bfloat16>(label_dtype, maps, a, n_images, c_max, s);
-    case MDSEG_F16: return launch<__half>(label_dtype, maps, a, n_images, c_max, s);
+    case MDSEG_F32: return launch<float>(label_dtype, maps, a, n_images, c_max, ents_fit, s);
+    case MDSEG_BF16: return launch<__nv_bfloat16>(label_dtype, maps, a, n_images, c_max, ents_fit, s);
+    case MDSEG_F16: return launch<__half>(label_dtype, maps, a, n_images, c_max, ents_fit, s);
   }
   return 2;
 }
@@ -818,10 +900,10 @@ extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t*
   a.sel8 = reinterpret_cast<uint8_t*>(a.lw2 + (size_t)n_images * H * W);
   tma::Maps maps;
   if (int rc = tma::make_maps(a.src, gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
-  switch (dst->dtype) {
-    case MDSEG_F32: return launch<float>(label_dtype, maps, a, n_images, c_max, s);
-    case MDSEG_BF16: return launch<__nv_bfloat16>(label_dtype, maps, a, n_images, c_max, s);
-    case MDSEG_F16: return launch<__half>(label_dtype, maps, a, n_images, c_max, s);
+  switch (dst->dtype) {  // identity channel lists: 16 entries per class group
+    case MDSEG_F32: return launch<float>(label_dtype, maps, a, n_images, c_max, true, s);
+    case MDSEG_BF16: return launch<__nv_bfloat16>(label_dtype, maps, a, n_images, c_max, true, s);
+    case MDSEG_F16: return launch<__half>(label_dtype, maps, a, n_images, c_max, true, s);
   }
   return 2;
 }

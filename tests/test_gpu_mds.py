@@ -80,6 +80,9 @@ GEOMS = [
     # (h, w, H, W): stride-4 crops, odd sizes, non-integer ratios, up to identity and down-sampling
     (16, 32, 64, 128), (24, 24, 96, 96), (7, 9, 25, 33), (33, 45, 130, 177), (8, 300, 29, 1200),
     (5, 6, 5, 6), (12, 10, 7, 9), (1, 1, 4, 4), (3, 140, 9, 520), (40, 40, 70, 70), (6, 8, 96, 128),
+    # w % 32 == 0: the backward runs as row CTAs (one warp per 32 columns, neighbours exchange the seam column):
+    # 2 / 3 / 5 / 16 warps, several 16-row segments, ratios with 4- and 5-pixel cells, a ratio below 4
+    (20, 64, 80, 256), (35, 96, 140, 384), (6, 160, 21, 608), (18, 512, 69, 2048), (9, 64, 45, 320),
 ]
 
 
@@ -100,12 +103,13 @@ def test_fp32_vs_f64_geometries(ops, geom, graph):
     assert rel_err(xd.grad.cpu().numpy(), ref["dlogits_uni"]) <= RTOL32
 
 
-@pytest.mark.parametrize("c_case", ["wide", "chunked"])
+@pytest.mark.parametrize("c_case", ["wide", "chunked", "wide_rows"])
 def test_many_classes_and_class_chunking(ops, c_case):
     """C_ds = 150 / 133 as in the 7-dataset config: exercises the staged class chunks of the fused kernels."""
-    n_cats, c_uni = ([150, 19, 133], 358) if c_case == "wide" else ([64, 37, 26], 127)
+    n_cats, c_uni = ([150, 19, 133], 358) if c_case.startswith("wide") else ([64, 37, 26], 127)
     ids = [0, 2, 1, 0]
-    x, graphs, labels = make_mds(77, n_cats, c_uni, ids, 10, 14, 37, 53, scale=2.0)
+    h, w, H, W = (10, 14, 37, 53) if c_case != "wide_rows" else (19, 64, 76, 256)  # row CTAs, 2 warps, 2 segments
+    x, graphs, labels = make_mds(77, n_cats, c_uni, ids, h, w, H, W, scale=2.0)
     thresh = ops.neg_log(0.4)
     ref = f64.multi_dataset(x.numpy(), labels.numpy(), np.array(ids), [m.numpy() for m in graphs], thresh)
     xd = x.to(DEV).requires_grad_(True)
@@ -233,7 +237,7 @@ def test_projection_alone_matches_einsum(ops):
         assert torch.equal(y[b, :n_cats[d]].cpu(), want)  # 0/1 graphs: exact
 
 
-@pytest.mark.parametrize("geom", [(16, 32, 64, 128), (9, 12, 36, 48), (7, 9, 25, 33)])
+@pytest.mark.parametrize("geom", [(16, 32, 64, 128), (9, 12, 36, 48), (7, 9, 25, 33), (20, 64, 80, 256)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_aux_heads_per_dataset_selection(ops, geom, dt):
     """Per-dataset aux heads (loss_cross_datasets.py:1044-1056): one OHEM selection per dataset, rows of other
