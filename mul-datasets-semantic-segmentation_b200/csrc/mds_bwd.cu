@@ -629,7 +629,10 @@ __global__ void __launch_bounds__(256) mds_bwd_fixup_kernel(const Args a) {
 }
 
 // cell-rows per unit: the per-unit set-up and the seam fix-up are amortised over 16 rows (8 and 30 measured within 3 %)
-int pick_seg_rows(int h) { return h - 1 < 16 ? h - 1 : 16; }
+#ifndef MDSEG_SEG_ROWS
+#define MDSEG_SEG_ROWS 16
+#endif
+int pick_seg_rows(int h) { return h - 1 < MDSEG_SEG_ROWS ? h - 1 : MDSEG_SEG_ROWS; }
 
 template <typename L>
 int launch_prep(const Args& a, int n_images, cudaStream_t s) {
