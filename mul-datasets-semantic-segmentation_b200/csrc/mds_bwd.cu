@@ -6,18 +6,21 @@
 // lib/loss/ohem_ce_loss.py:61-90): log_softmax_backward over [B_i,C_ds,H,W], upsample_bilinear2d
 // backward (scatter), the einsum backward (bmm) and the index_put into [ΣB,C_uni,h,w].
 //
-// Work decomposition — one WARP per unit, nothing shared between warps (CTA = 32 threads):
-//   unit = (image b, class group of 16 dataset classes, strip of 28 low-res columns,
-//           segment of `seg_rows` cell-rows);  a cell-row g interpolates between low-res rows g, g+1.
-//   lane l <= 28 owns cell x = 28*strip + l - 1 (lane 0 is the left halo cell) and, for l >= 1, column x;
-//   the strip width is a multiple of four columns so that finished rows leave as 16-byte stores.
-//   * the class planes of rows (g, g+1) arrive as 4-D TMA boxes [16 classes][2 rows][36 cols]
-//     in a 3-stage mbarrier ring (lane 0 issues, nobody copies);
+// Work decomposition — one WARP per unit = (image b, class group of 16 dataset classes, strip of low-res columns,
+// segment of `seg_rows` cell-rows); a cell-row g interpolates between low-res rows g, g+1.  Two layouts (template ROW):
+//   ROW  (w % 32 == 0, w <= 512): the CTA is the w / 32 warps of a row segment, warp i owns columns 32i .. 32i+31 and
+//        lane l owns cell x = 32i + l AND column x; the right-column sums of lane 31 reach lane 0 of the next warp
+//        through a two-slot shared-memory exchange guarded by full / empty mbarriers (see Lay<ROW> and cell_row);
+//   !ROW (any other width): the CTA is one warp owning 28 columns; lane l <= 28 owns cell x = 28*strip + l - 1 (lane 0
+//        is the left halo cell, recomputed) and, for l >= 1, column x; nothing is shared between warps.
+//   In both the strip width is a multiple of four columns so that finished rows leave as 16-byte stores.
+//   * the class planes of rows (g, g+1) arrive as 4-D TMA boxes [8 classes][2 rows][36 cols]
+//     in a 2-stage mbarrier ring (lane 0 issues, nobody copies);
 //   * per (pixel, class): w*softmax = ex2(z*log2e + (log2 w - lse2)), with the 4..5 x 4..5 label pixels
 //     of the cell in registers and the arithmetic packed two columns per instruction (FFMA2/FADD2);
 //     per class the cell reduces to 4 sums (upper/lower row x own/right column); the right-column
 //     part moves one lane up by shuffle;
-//   * the -w*[c == label] term is a shared-memory scatter per pixel (two phases, no atomics);
+//   * the -w*[c == label] term is one packed fp16 compare and two predicated adds per pixel pair;
 //   * vertical: the lower-row sums of cell-row g are carried in shared memory and added to the
 //     upper-row sums of cell-row g+1, so every low-res row inside a segment is final when it
 //     leaves the warp and is broadcast to the unified channels of its class (CSR walk of G, or the
