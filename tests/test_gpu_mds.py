@@ -163,10 +163,11 @@ def test_invalid_dataset_id_is_skipped_and_flagged(ops):
         ops.check_errors(DEV)
 
 
+@pytest.mark.parametrize("geom", [(16, 24, 64, 96), (18, 64, 72, 256)])  # one-warp CTAs / row CTAs
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-def test_half_precision_logits(ops, dt):
+def test_half_precision_logits(ops, dt, geom):
     n_cats, c_uni, ids = [5, 3, 7], 11, [0, 1, 2, 2]
-    x, graphs, labels = make_mds(3, n_cats, c_uni, ids, 16, 24, 64, 96)
+    x, graphs, labels = make_mds(3, n_cats, c_uni, ids, *geom)
     thresh = ops.neg_log(0.4)
     xq = x.to(dt)
     ref_q = f64.multi_dataset(xq.float().numpy(), labels.numpy(), np.array(ids), [m.numpy() for m in graphs], thresh)
