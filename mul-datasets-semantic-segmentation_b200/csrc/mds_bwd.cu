@@ -509,28 +509,44 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
     }
   }
   for (int cg = 0; cg < kCG; ++cg) carry[cg * 32 + lane] = 0.f;
-  // (class, output channel) pairs of this class group, chunk by chunk, each chunk padded to whole quads
+  // (class, output channel) pairs of this class group, chunk by chunk, each chunk padded to whole quads.  The CSR row
+  // starts of the group's classes are fetched by lanes 0..16 in one round trip and the channel ids 32 at a time (a
+  // class-by-class walk costs two dependent global loads per class, ~30 round trips during which a row CTA — whose
+  // warps all start together — leaves the SM idle).
+  static_assert(kCG == 2 * kKC, "the channel-list cache is laid out for two chunks per class group");
   if ((gd.csr_ptr == nullptr || gd.csr_val == nullptr) && a.out_channels[d] <= 0xffff &&
       (int64_t)a.out_channels[d] * h * w < 0x7fffffffLL) {
-    int pos = 0;
-    for (int k = 0; k < un.n_ch; ++k) {
-      if (lane == 0) eptr[k] = pos >> 2;
-      for (int j = 0; j < kKC && c_beg + k * kKC + j < c_end; ++j) {
-        const int cls = c_beg + k * kKC + j;
-        int e0 = cls, e1 = cls + 1;
-        if (gd.csr_ptr != nullptr) { e0 = __ldg(gd.csr_ptr + cls); e1 = __ldg(gd.csr_ptr + cls + 1); }
-        for (int e = e0 + lane; e < e1; e += 32) {
-          const int u = gd.csr_ptr != nullptr ? __ldg(gd.csr_col + e) : cls;
-          if (pos + (e - e0) < kEnt) ents[pos + (e - e0)] = (uint32_t)u | ((uint32_t)j << 16);
-        }
-        pos += e1 - e0;
-      }
-      const int padded = (pos + 3) & ~3;
-      if (lane < padded - pos && pos + lane < kEnt) ents[pos + lane] = kNoEnt;
-      pos = padded;
+    const int ncls = c_end - c_beg, nc0 = ncls < kKC ? ncls : kKC;
+    int myptr = c_beg + lane;  // identity: entry e is class c_beg + e
+    if (gd.csr_ptr != nullptr) myptr = lane <= ncls ? __ldg(gd.csr_ptr + c_beg + lane) : 0;
+    const int p0 = __shfl_sync(0xffffffffu, myptr, 0);
+    const int p8 = __shfl_sync(0xffffffffu, myptr, nc0);
+    const int pe = __shfl_sync(0xffffffffu, myptr, ncls);
+    const int len0 = p8 - p0, len1 = pe - p8;
+    const int base1 = (len0 + 3) & ~3;
+    const int total = base1 + ((len1 + 3) & ~3);
+    if (lane == 0) {
+      eptr[0] = 0;
+      eptr[1] = base1 >> 2;
+      eptr[un.n_ch] = total >> 2;  // n_ch == 1: len1 == 0 and total == base1
     }
-    if (lane == 0) eptr[un.n_ch] = pos >> 2;
-    un.cached = pos <= kEnt;
+    for (int eb = 0; eb < pe - p0; eb += 32) {
+      const int e = eb + lane;
+      int cls = 0;  // class of entry e within the group: number of row starts (classes 1..ncls-1) at or below it
+#pragma unroll
+      for (int j = 1; j < kCG; ++j) {
+        const int pj = __shfl_sync(0xffffffffu, myptr, j);
+        cls += (j < ncls && pj <= p0 + e) ? 1 : 0;
+      }
+      if (e < pe - p0) {
+        const int u = gd.csr_ptr != nullptr ? __ldg(gd.csr_col + p0 + e) : c_beg + e;
+        const int pos = cls < kKC ? e : base1 + (e - len0);
+        if (pos < kEnt) ents[pos] = (uint32_t)u | ((uint32_t)(cls & (kKC - 1)) << 16);
+      }
+    }
+    if (lane < base1 - len0 && len0 + lane < kEnt) ents[len0 + lane] = kNoEnt;
+    if (lane < total - base1 - len1 && base1 + len1 + lane < kEnt) ents[base1 + len1 + lane] = kNoEnt;
+    un.cached = total <= kEnt;
   }
   __syncwarp();
   if (ROW) __syncthreads();  // the neighbours' exchange barriers are initialised (every early exit above is CTA-uniform)
