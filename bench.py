@@ -34,12 +34,15 @@ WORKLOADS = {
     "cfg3": ([19, 64, 37, 19, 26, 150, 133], 358, [0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6], (256, 512), (1024, 2048)),
     "cfg2": ([19, 12, 36], 67, [0] * 5 + [1] * 5 + [2] * 6, (256, 512), (1024, 2048)),
     "cfg1": ([19], 19, [0, 0], (128, 256), (512, 1024)),
+    # the repo's own per-GPU batch of that config: crop 768 x 768, ims_per_gpu 4 for each of the 7 datasets
+    "cfg3_native": ([19, 64, 37, 19, 26, 150, 133], 358, [d for d in range(7) for _ in range(4)], (192, 192), (768, 768)),
     "tiny": ([5, 3, 7], 11, [0, 1, 2, 2], (16, 32), (64, 128)),
 }
 WORKLOAD_NAMES = {
     "cfg3": "ltbgnn_7_datasets_snp: 7-dataset unified label space (C_uni 358), per-GPU batch 16x1024x2048, logits 256x512",
     "cfg2": "ltbgnn_city_cam_a2d2: 3 datasets (C_uni 67), per-GPU batch 16x1024x2048, logits 256x512",
     "cfg1": "bisenetv2_city-sized: 1 dataset 19 classes, batch 2x512x1024, logits 128x256",
+    "cfg3_native": "ltbgnn_7_datasets_snp at the repo's own crop: 7 datasets x 4 images of 768x768, logits 192x192",
     "tiny": "tiny self-test",
 }
 
