@@ -50,28 +50,26 @@ proj_fwd_sparse_kernel(const T* __restrict__ x, const mdseg_graph_table tab, con
 #pragma unroll
       for (int i = 0; i < PX; ++i) acc[i] = 0.f;
       const int j0 = __ldg(g.csr_ptr + n), j1 = __ldg(g.csr_ptr + n + 1);
-      int j = j0;
-      for (; j + 4 <= j1; j += 4) {  // 4 planes in flight
-        float v[4][PX];
-        float wv[4];
+      // up to 8 planes of a class in flight at once (predicated), accumulated in CSR order: a class of the 7-dataset
+      // graphs has 5.9 unified channels on average, so most classes cost one memory round trip instead of 1 + (n mod 4)
+      for (int j = j0; j < j1; j += 8) {
+        float v[8][PX];
+        float wv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = __ldg(g.csr_col + j + u);
-          wv[u] = g.csr_val ? __ldg(g.csr_val + j + u) : 1.f;
-          VecLoad<T, PX>::load(xb + (int64_t)c * hw + p, v[u]);
+        for (int u = 0; u < 8; ++u) {
+          if (j + u < j1) {
+            const int c = __ldg(g.csr_col + j + u);
+            wv[u] = g.csr_val ? __ldg(g.csr_val + j + u) : 1.f;
+            VecLoad<T, PX>::load(xb + (int64_t)c * hw + p, v[u]);
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u) {
+          if (j + u < j1) {
 #pragma unroll
-          for (int i = 0; i < PX; ++i) acc[i] = fmaf(wv[u], v[u][i], acc[i]);
-      }
-      for (; j < j1; ++j) {
-        const int c = __ldg(g.csr_col + j);
-        const float wv = g.csr_val ? __ldg(g.csr_val + j) : 1.f;
-        float v[PX];
-        VecLoad<T, PX>::load(xb + (int64_t)c * hw + p, v);
-#pragma unroll
-        for (int i = 0; i < PX; ++i) acc[i] = fmaf(wv, v[i], acc[i]);
+            for (int i = 0; i < PX; ++i) acc[i] = fmaf(wv[u], v[u][i], acc[i]);
+          }
+        }
       }
       float* dst = yb + (int64_t)n * hw + p;
 #pragma unroll
