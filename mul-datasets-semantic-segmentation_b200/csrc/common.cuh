@@ -110,12 +110,15 @@ __device__ __forceinline__ void stg_stream_v4(void* p, int4 v) {
 // Load V consecutive elements of type T (V*sizeof(T) is 4, 8 or 16 bytes,
 // pointer aligned accordingly) and widen to fp32.
 template <typename T, int V> struct VecLoad;
+// raw(): the load alone (what is kept in registers while several loads are in flight); unpack(): raw -> fp32
 template <> struct VecLoad<float, 4> {
-  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
-    int4 r = ldg_stream_v4(p);
+  using Raw = int4;
+  static __device__ __forceinline__ Raw raw(const float* p) { return ldg_stream_v4(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[4]) {
     o[0] = __int_as_float(r.x); o[1] = __int_as_float(r.y);
     o[2] = __int_as_float(r.z); o[3] = __int_as_float(r.w);
   }
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) { unpack(raw(p), o); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     int4 r = make_int4(__float_as_int(v[0]), __float_as_int(v[1]),
                        __float_as_int(v[2]), __float_as_int(v[3]));
@@ -123,12 +126,17 @@ template <> struct VecLoad<float, 4> {
   }
 };
 template <> struct VecLoad<float, 1> {
+  using Raw = float;
+  static __device__ __forceinline__ Raw raw(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[1]) { o[0] = r; }
   static __device__ __forceinline__ void load(const float* p, float (&o)[1]) { o[0] = __ldg(p); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { p[0] = v[0]; }
 };
 template <> struct VecLoad<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
-    int4 r = ldg_stream_v4(p);
+  using Raw = int4;
+  static __device__ __forceinline__ Raw raw(const __nv_bfloat16* p) { return ldg_stream_v4(p); }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) { unpack(raw(p), o); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[8]) {
     const uint32_t w[4] = {(uint32_t)r.x, (uint32_t)r.y, (uint32_t)r.z, (uint32_t)r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -147,12 +155,17 @@ template <> struct VecLoad<__nv_bfloat16, 8> {
   }
 };
 template <> struct VecLoad<__nv_bfloat16, 1> {
+  using Raw = __nv_bfloat16;
+  static __device__ __forceinline__ Raw raw(const __nv_bfloat16* p) { return *p; }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[1]) { o[0] = __bfloat162float(r); }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[1]) { o[0] = __bfloat162float(*p); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { p[0] = __float2bfloat16_rn(v[0]); }
 };
 template <> struct VecLoad<__half, 8> {
-  static __device__ __forceinline__ void load(const __half* p, float (&o)[8]) {
-    int4 r = ldg_stream_v4(p);
+  using Raw = int4;
+  static __device__ __forceinline__ Raw raw(const __half* p) { return ldg_stream_v4(p); }
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[8]) { unpack(raw(p), o); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[8]) {
     const uint32_t w[4] = {(uint32_t)r.x, (uint32_t)r.y, (uint32_t)r.z, (uint32_t)r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -172,6 +185,9 @@ template <> struct VecLoad<__half, 8> {
   }
 };
 template <> struct VecLoad<__half, 1> {
+  using Raw = __half;
+  static __device__ __forceinline__ Raw raw(const __half* p) { return *p; }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[1]) { o[0] = __half2float(r); }
   static __device__ __forceinline__ void load(const __half* p, float (&o)[1]) { o[0] = __half2float(*p); }
   static __device__ __forceinline__ void store(__half* p, const float (&v)[1]) { p[0] = __float2half_rn(v[0]); }
 };

@@ -52,22 +52,26 @@ proj_fwd_sparse_kernel(const T* __restrict__ x, const mdseg_graph_table tab, con
       const int j0 = __ldg(g.csr_ptr + n), j1 = __ldg(g.csr_ptr + n + 1);
       // up to 8 planes of a class in flight at once (predicated), accumulated in CSR order: a class of the 7-dataset
       // graphs has 5.9 unified channels on average, so most classes cost one memory round trip instead of 1 + (n mod 4)
+      // (the loads stay in their 16-byte raw form until they are accumulated: widening eight bf16 planes to fp32 up
+      // front costs 64 registers and most of the occupancy)
       for (int j = j0; j < j1; j += 8) {
-        float v[8][PX];
+        typename VecLoad<T, PX>::Raw raw[8];
         float wv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (j + u < j1) {
             const int c = __ldg(g.csr_col + j + u);
             wv[u] = g.csr_val ? __ldg(g.csr_val + j + u) : 1.f;
-            VecLoad<T, PX>::load(xb + (int64_t)c * hw + p, v[u]);
+            raw[u] = VecLoad<T, PX>::raw(xb + (int64_t)c * hw + p);
           }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (j + u < j1) {
+            float v[PX];
+            VecLoad<T, PX>::unpack(raw[u], v);
 #pragma unroll
-            for (int i = 0; i < PX; ++i) acc[i] = fmaf(wv[u], v[u][i], acc[i]);
+            for (int i = 0; i < PX; ++i) acc[i] = fmaf(wv[u], v[i], acc[i]);
           }
         }
       }
