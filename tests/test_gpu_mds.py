@@ -120,11 +120,35 @@ def test_many_classes_and_class_chunking(ops, c_case):
     assert rel_err(xd.grad.cpu().numpy(), ref["dlogits_uni"]) <= RTOL32
 
 
-def test_topk_branch_of_the_fused_path(ops):
+@pytest.mark.parametrize("geom", [(12, 16, 48, 64), (19, 64, 76, 256)])  # one-warp CTAs / row CTAs
+def test_unified_classes_without_a_dataset_class_get_zero_gradient(ops, geom):
+    """UOT / pretrain graphs leave some unified classes unmapped for a dataset (empty CSC columns): their channels
+    of dlogits_uni must be written as zeros by the fused backward (the output buffer is uninitialised)."""
+    h, w, H, W = geom
+    n_cats, c_uni, ids = [5, 3, 7], 13, [2, 0, 1, 2]
+    x, graphs, labels = make_mds(9, n_cats, c_uni, ids, h, w, H, W)
+    for d, m in enumerate(graphs):
+        m[:, [1 + d, 8, 12]] = 0  # unmapped unified classes (every dataset class keeps a channel: :c_ds are identity)
+        m[:, 0] = 0
+        m[0, 0] = 1
+    thresh = ops.neg_log(0.4)
+    ref = f64.multi_dataset(x.numpy(), labels.numpy(), np.array(ids), [m.numpy() for m in graphs], thresh)
+    xd = x.to(DEV).requires_grad_(True)
+    torch.empty(1 << 22, device=DEV).fill_(float("nan"))  # poison the allocator's free blocks
+    loss = ops.mds_proj_ohem_ce(xd, labels.to(DEV), torch.tensor(ids, device=DEV), [m.to(DEV) for m in graphs], thresh)
+    loss.backward()
+    ops.check_errors(DEV)
+    assert abs(float(loss) - ref["loss"]) <= RTOL32 * abs(ref["loss"])
+    assert rel_err(xd.grad.cpu().numpy(), ref["dlogits_uni"]) <= RTOL32
+    assert float(xd.grad[:, 8].abs().max()) == 0.0 and float(xd.grad[:, 12].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("geom", [(12, 16, 48, 64), (19, 64, 76, 256)])  # one-warp CTAs / row CTAs
+def test_topk_branch_of_the_fused_path(ops, geom):
     """Confident predictions: fewer hard pixels than n_min -> device-side top-k fallback."""
     n_cats, c_uni, ids = [5, 3, 7], 15, [0, 1, 2, 2]
     g = torch.Generator().manual_seed(1)
-    B, h, w, H, W = 4, 12, 16, 48, 64
+    B, (h, w, H, W) = 4, geom
     graphs = [onehot_graph(g, c, c_uni) for c in n_cats]
     x = torch.randn(B, c_uni, h, w, generator=g) * 0.3
     labels = torch.empty(B, H, W, dtype=torch.long)
@@ -146,12 +170,13 @@ def test_topk_branch_of_the_fused_path(ops):
     assert rel_err(xd.grad.cpu().numpy(), ref["dlogits_uni"]) <= 5e-5
 
 
-def test_invalid_dataset_id_is_skipped_and_flagged(ops):
+@pytest.mark.parametrize("geom", [(8, 8, 32, 32), (8, 64, 32, 256)])  # one-warp CTAs / row CTAs
+def test_invalid_dataset_id_is_skipped_and_flagged(ops, geom):
     """An image whose dataset id matches no dataset takes no part in the loss (ohem_ce_loss.py:58-59) but its
     labels still count in n_min (:52); it gets a zero gradient."""
     n_cats, c_uni, ids = [5, 3], 9, [0, 7, 1]
-    x, graphs, labels = make_mds(5, n_cats, c_uni, ids, 8, 8, 32, 32)
-    labels[1] = torch.randint(0, 3, (32, 32))
+    x, graphs, labels = make_mds(5, n_cats, c_uni, ids, *geom)
+    labels[1] = torch.randint(0, 3, geom[2:])
     thresh = ops.neg_log(0.4)
     ref = f64.multi_dataset(x.numpy(), labels.numpy(), np.array(ids), [m.numpy() for m in graphs], thresh)
     xd = x.to(DEV).requires_grad_(True)
