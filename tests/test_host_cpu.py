@@ -151,3 +151,23 @@ def test_world_size_2_gloo(tmp_path):
     s.close()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_label_transform_planner_draws_the_reference_stream():
+    """dropin.label_transform (host side of ops.label_pipeline) makes the same np.random draws in the same order as
+    the restated RandomResizedCrop / RandomHorizontalFlip / ColorJitter sequence that tests/test_oracle_golden.py pins
+    on the real lib/transform_cv2.py: same seed -> same plans, and the streams stay aligned over many samples."""
+    import numpy as np
+    from mdseg_b200.dropin.label_transform import LabelPipeline
+    from oracle import label_space as ls
+    shapes = [(96, 160), (1100, 1200), (1090, 1085), (300, 700), (64, 96), (2000, 1500)] * 3
+    for scales, size, seed in (((0.5, 1.0), (64, 96), 1), ((0.03, 0.06), (64, 96), 2), ((0.75, 2.0), (256, 512), 3)):
+        pipe = LabelPipeline(scales, size, p=0.5)
+        got = pipe.plans(shapes, np.random.RandomState(seed))
+        rng = np.random.RandomState(seed)
+        for shape, g in zip(shapes, got):
+            want = ls.plan_random_resized_crop(shape, scales, size, rng)
+            want["flip"] = not (rng.random() < 0.5)
+            for _ in range(3):
+                rng.uniform(0.0, 1.0)
+            assert g == want, (shape, g, want)
