@@ -452,6 +452,35 @@ typedef struct mdseg_label_view {
 int mdseg_label_pipeline(const mdseg_label_view* views /*device*/, int n_images, const uint8_t* luts, int n_luts,
                          void* out, int out_dtype, int out_h, int out_w, int pad_value, void* stream);
 
+/* ---- f4: NLLPlus loss (soft-max in the unified space, projection of PROBABILITIES, up-sampling, -log) ----------
+ * Replaces AdjNLLPlusLoss.forward (lib/loss/loss_helper.py:647-668) as driven by MdsOhemNLLPlusLoss
+ * (lib/loss/ohem_ce_loss.py:92-146):
+ *     pred  = softmax(x, dim=1)                                   mdseg_softmax_nchw
+ *     probs = einsum('bchw,nc->bnhw', pred, Adj)                  mdseg_proj_fwd on `pred`
+ *     probs = F.interpolate(probs, label size, bilinear, align_corners=True);  loss = -log(probs)[label]
+ *                                                                 mdseg_up_nll_fwd (no [B,C,H,W] tensor)
+ * then mdseg_ohem_select on loss_px, and backward:
+ *     d loss / d probs_low                                        mdseg_up_nll_bwd (tent gather, no atomics)
+ *     d loss / d pred = Adj^T (.)                                 mdseg_proj_bwd
+ *     d loss / d x    = pred * (dpred - sum_c pred_c dpred_c)     mdseg_softmax_bwd_nchw */
+/* pred[b, c, p] = softmax_c x[b, :, p];  x: [n_images, C, hw] of `dtype`, pred fp32 */
+int mdseg_softmax_nchw(const void* x, int dtype, int n_images, int C, int64_t hw, float* pred, void* stream);
+/* dx[b, c, p] = pred * (dpred - sum_c pred * dpred);  dx of dx_dtype, may alias dpred when fp32 */
+int mdseg_softmax_bwd_nchw(const float* pred, const float* dpred, int n_images, int C, int64_t hw, void* dx,
+                           int dx_dtype, void* stream);
+/* loss_px[b, Y, X] = -log(bilinear_ac(src[d][b, label])(Y, X)), 0 for ignored pixels, -1 for images of no dataset;
+ * OHEM counters (n_valid, n_hard, sum_hard, n_px) are accumulated into the image's segment as mdseg_up_ce_fwd does.
+ * src: fp32 projected probabilities (layout as mdseg_src_table). */
+int mdseg_up_nll_fwd(const mdseg_src_table* src /*host*/, const int32_t* dataset_ids, const void* labels,
+                     int label_dtype, int n_images, int h, int w, int H, int W, int ignore, float* loss_px,
+                     mdseg_ohem_state* states, int32_t* err_flag, void* stream);
+/* dst[d][b, n, y, x] += sum over selected label pixels of class n under the tent of (y, x) of -w * tent / prob;
+ * dst: fp32 planes shaped like src, ZERO-INITIALISED by the caller; w = grad_out[seg] * grad_scale / |S|. */
+int mdseg_up_nll_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset_ids, const void* labels,
+                     int label_dtype, int n_images, int h, int w, int H, int W, int ignore, const float* loss_px,
+                     const mdseg_ohem_state* states, const float* grad_out, float grad_scale,
+                     const mdseg_src_table* dst /*host*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,12 +27,19 @@ using namespace tma;
 
 constexpr int kKC = 8;                          // classes per TMA stage
 constexpr int kBoxW = 36;                       // staged columns: 33 needed, rows of 144 B
-constexpr int kStages = 3;
+#ifndef MDSEG_FWD_STAGES
+#define MDSEG_FWD_STAGES 3
+#endif
+constexpr int kStages = MDSEG_FWD_STAGES;
 constexpr int kStageFloats = kKC * 2 * kBoxW;   // 576
 constexpr int kStageBytes = kStageFloats * 4;   // 2304
 constexpr int kStgW = 176;                      // staged label columns: <= 15 alignment + 32 cells x 5
 constexpr int kMaxR = 5;
 constexpr int kSpan = 160;
+#ifndef MDSEG_FWD_RECUR
+#define MDSEG_FWD_RECUR 0
+#endif
+constexpr float kRecurMaxDd = 80.f;             // log2 units per cell: beyond it the row recurrence is not used
 
 struct Args {
   mdseg_src_table src;
@@ -110,6 +117,8 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     LH[j][0] = hv[0] | (hv[1] << 16);
     LH[j][1] = hv[2] | (hv[3] << 16);
     lh4[j] = hv[4] | (0x5bf8u << 16);
+    // keep the packed form live: under register pressure ptxas otherwise re-packs the halves inside the class loop
+    asm volatile("" : "+r"(LH[j][0]), "+r"(LH[j][1]));
   }
   // per-corner channel maxima (already in log2 units), and their interpolation M per pixel column
   const float c00 = cms[un.xl] * kLog2e, c01 = cms[un.xl + 1] * kLog2e;
@@ -122,6 +131,22 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
   for (int j = 0; j < RT; ++j) L1H[j] = dup2(l1h[j]);
   const float2 L1W[2] = {make_float2(l1w[0], l1w[1]), make_float2(l1w[2], l1w[3])};
   const float l1w4 = l1w[4];
+#if MDSEG_FWD_RECUR
+  // row-weight step dh = l1h[1] - l1h[0] (exact in fp32: both are differences of source coordinates inside one cell)
+  // and the deviation eta_j of the later steps from it, premultiplied by ln 2
+  float dh = l1h[1] - l1h[0];
+  float kj[RT];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    kj[j] = j >= 2 ? ((l1h[j] - l1h[j - 1]) - dh) * kLn2 : 0.f;
+    asm volatile("" : "+f"(kj[j]));  // computed once per cell-row, not re-derived per class
+  }
+  asm volatile("" : "+f"(dh));
+  const float2 DH2 = dup2(dh);
+  float2 KJ[RT];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) KJ[j] = dup2(kj[j]);
+#endif
 
   float2 S[RT][2], T[RT][2];
   float s4[RT], t4[RT];
@@ -149,6 +174,52 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       Sp += 2 * kBoxW;
       const float dv0 = v01 - v00, dv1 = v11 - v10;
       const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
+#if MDSEG_FWD_RECUR
+      // Row recurrence: inside a column the exponent is linear in the row weight, so the exponentials of rows
+      // 1.. follow from row 0 by one ratio r = 2^(dh * dd) per column — two MUFU.EX2 per column instead of one
+      // per pixel.  ATen's fp32 row weights are not an exact progression (|eta_j| <= one ulp of the source
+      // coordinate, ~1.5e-5): the ratio of step j is r * 2^(eta_j dd) = r + (ln2 eta_j)(r dd) to first order
+      // (second-order term <= 6e-7 for |dd| <= kRecurMaxDd; steeper columns take the per-pixel path below).
+      const float steep = fmaxf(fabsf(v10 - v00), fabsf(v11 - v01));
+      if (!__any_sync(0xffffffffu, steep > kRecurMaxDd)) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const float2 h0 = fma2(L1W[p], DV0, V0);
+          const float2 dd = sub2(fma2(L1W[p], DV1, V1), h0);
+          const float2 a0 = fma2(L1H[0], dd, h0);
+          float2 E = ex2_2(a0);
+          const float2 r = ex2_2(mul2(DH2, dd));
+          const float2 rd = mul2(r, dd);
+          pick_label2(T[0][p], a0, LH[0][p], c2);
+          S[0][p] = add2(S[0][p], E);
+#pragma unroll
+          for (int j = 1; j < RT; ++j) {
+            const float2 arg = fma2(L1H[j], dd, h0);
+            pick_label2(T[j][p], arg, LH[j][p], c2);
+            E = mul2(E, j == 1 ? r : fma2(KJ[j], rd, r));
+            S[j][p] = add2(S[j][p], E);
+          }
+        }
+        if (NX5) {
+          const float h0 = fmaf(l1w4, dv0, v00);
+          const float dd = fmaf(l1w4, dv1, v10) - h0;
+          const float a0 = fmaf(l1h[0], dd, h0);
+          float E = ex2_approx(a0);
+          const float r = ex2_approx(DH2.x * dd);
+          const float rd = r * dd;
+#pragma unroll
+          for (int j = 0; j < RT; ++j) {
+            const float arg = j == 0 ? a0 : fmaf(l1h[j], dd, h0);
+            float2 t = make_float2(t4[j], 0.f);
+            pick_label2(t, make_float2(arg, 0.f), lh4[j], c2);
+            t4[j] = t.x;
+            if (j >= 1) E *= (j == 1 ? r : fmaf(KJ[j].x, rd, r));
+            s4[j] += E;
+          }
+        }
+        continue;
+      }
+#endif
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const float2 h0 = fma2(L1W[p], DV0, V0);
@@ -223,7 +294,10 @@ constexpr size_t kOffBars = kOffRb + 2 * kSpan * 4;
 constexpr size_t kSmem = kOffBars + (kStages + 1) * 8;
 static_assert(kOffCm % 128 == 0 && kOffLab % 16 == 0 && kOffRb % 16 == 0 && kOffBars % 8 == 0, "smem carve-up");
 
-__global__ void __launch_bounds__(32, 14) up_ce_fwd_warp_kernel(const __grid_constant__ Maps maps,
+#ifndef MDSEG_FWD_OCC
+#define MDSEG_FWD_OCC 14
+#endif
+__global__ void __launch_bounds__(32, MDSEG_FWD_OCC) up_ce_fwd_warp_kernel(const __grid_constant__ Maps maps,
                                                                 const __grid_constant__ CUtensorMap cmap,
                                                                 const __grid_constant__ Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

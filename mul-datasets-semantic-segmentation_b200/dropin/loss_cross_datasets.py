@@ -1,5 +1,9 @@
-"""Drop-in for lib/loss/loss_cross_datasets.py ``CrossDatasetsCELoss_AdvGNN`` (:812-1138) — the loss class the
-``ltbgnn_*`` configs select with ``loss.type = "Adv_GNN"`` — in every stage the trainer calls it in.
+"""Drop-in for lib/loss/loss_cross_datasets.py: ``CrossDatasetsCELoss_AdvGNN`` (:812-1138) — the loss class the
+``ltbgnn_*`` configs select with ``loss.type = "Adv_GNN"`` — in every stage the trainer calls it in, plus
+``CrossDatasetsCELoss`` (:303-347), ``CrossDatasetsCELoss_CLIP`` (:662-712) and ``CrossDatasetsCELoss_GNN`` (:714-776)
+on the same fused kernels.  Every other name of the reference module (``CrossDatasetsLoss``,
+``CrossDatasetsCELoss_KMeans``, ``CrossDatasetsCELoss_AdvGNN_ce`` ...) is passed through from the reference's own file
+(``_reference.py``), so the trainers' import line (tools/train_ltbgnn_all_datasets_snp.py:28) works unchanged.
 
 ``forward(preds, target, dataset_ids, is_adv=True, init_gnn_stage=False) -> (loss, orth_loss, aux_loss, adj_loss)``
 
@@ -26,7 +30,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .ohem_ce_loss import MdsOhemCELoss, OhemCELoss
+from . import _reference
+from .class_remap import ClassRemap, ClassRemapOneHotLabel  # noqa: F401  (configs name them: eval(class_remaper))
+from .ohem_ce_loss import MdsOhemCELoss, MdsOhemNLLPlusLoss, OhemCELoss  # noqa: F401
 
 
 def _cfg(configer, *key, default=None):
@@ -36,6 +42,142 @@ def _cfg(configer, *key, default=None):
         return configer.get(*key)
     except (KeyError, TypeError):
         return default
+
+
+def LabelToOneHot(LabelVector, nClass, ignore_index=-1):
+    """:18-26 — bool [len, nClass] one-hot of a 1-D label vector (rows of ignored labels stay empty)."""
+    out = torch.zeros(len(LabelVector), nClass, dtype=torch.bool, device=LabelVector.device)
+    keep = LabelVector != ignore_index
+    out[keep, LabelVector[keep]] = 1
+    return out
+
+
+def _present_rows(dataset_ids, n_datasets):
+    ids = torch.as_tensor(dataset_ids).reshape(-1).tolist()  # the one host read of a forward
+    return [[b for b, v in enumerate(ids) if int(v) == i] for i in range(n_datasets)]
+
+
+def _sum_present(per_dataset, present):
+    """Sum of the entries of `per_dataset` [n_datasets] whose dataset has images (the reference skips the others,
+    e.g. :333-334); None when the batch is empty."""
+    idx = [i for i, rows in enumerate(present) if rows]
+    if not idx:
+        return None
+    return per_dataset[torch.tensor(idx, device=per_dataset.device)].sum()
+
+
+class CrossDatasetsCELoss(nn.Module):
+    """:303-347 — remap-matrix projection of the unified logits (ClassRemap.getRemapMatrix) + plain cross-entropy
+    (ignore 255) per dataset, summed over the datasets present.  Pinned by the reference's own known-answer test
+    (lib/loss/test/test_loss_cross_datasets.py:118-145, 5.106813430786133)."""
+
+    def __init__(self, configer=None):
+        super().__init__()
+        self.configer = configer
+        self.n_datasets = self.configer.get('n_datasets')
+        self.classRemapper = eval(self.configer.get('class_remaper'))(configer=self.configer)
+        self.num_unify_classes = self.configer.get('num_unify_classes')
+        self.num_prototype = _cfg(configer, 'contrast', 'num_prototype')
+        self.temperature = _cfg(configer, 'contrast', 'temperature')
+        self.with_mulbn = _cfg(configer, 'contrast', 'with_mulbn')
+        self.reweight = _cfg(configer, 'loss', 'reweight')
+        self.ignore_index = _cfg(configer, 'loss', 'ignore_index', default=255)
+        self.n_cats = [configer.get('dataset' + str(i), 'n_cats') for i in range(1, self.n_datasets + 1)]
+        self.CELoss = torch.nn.CrossEntropyLoss(ignore_index=255)  # kept for introspection only
+        self._graph_cache = ops.BipartiteGraphs()
+        self._matrices = None
+
+    def forward(self, preds, target, dataset_ids, is_warmup=False):
+        self.with_aux = self.configer.get('loss', 'with_aux')
+        logits = preds['seg'][0] if self.with_aux else preds['seg']
+        if self._matrices is None or self._matrices[0].device != logits.device:
+            self._matrices = [self.classRemapper.getRemapMatrix(i).to(logits.device) for i in range(self.n_datasets)]
+        present = _present_rows(dataset_ids, self.n_datasets)
+        per_ds = ops.mds_proj_ce_mean(logits, target, dataset_ids, self._matrices, ignore=255, cache=self._graph_cache)
+        return _sum_present(per_ds, present)
+
+
+class CrossDatasetsCELoss_CLIP(nn.Module):
+    """:662-712 — text-prototype head (optional), per-dataset projection (remap matrix or the dataset's text
+    features), bilinear up-sampling to the label size and OhemCELoss(0.7) per dataset, summed."""
+
+    def __init__(self, configer=None):
+        super().__init__()
+        self.configer = configer
+        self.n_datasets = self.configer.get('n_datasets')
+        self.num_prototype = _cfg(configer, 'contrast', 'num_prototype')
+        self.temperature = _cfg(configer, 'contrast', 'temperature')
+        self.with_mulbn = _cfg(configer, 'contrast', 'with_mulbn')
+        self.reweight = _cfg(configer, 'loss', 'reweight')
+        self.ignore_index = _cfg(configer, 'loss', 'ignore_index', default=255)
+        self.with_unify_label = self.configer.get('loss', 'with_unify_label')
+        if self.with_unify_label:
+            self.classRemapper = eval(self.configer.get('class_remaper'))(configer=self.configer)
+        self.n_cats = [configer.get('dataset' + str(i), 'n_cats') for i in range(1, self.n_datasets + 1)]
+        self.CELoss = OhemCELoss(0.7, ignore_lb=255)
+        self._graph_cache = ops.BipartiteGraphs()
+        self._matrices = None
+
+    def forward(self, preds, target, dataset_ids, is_warmup=False):
+        logits = preds['seg']
+        text_feature_vecs = preds['prototypes']
+        if self.with_unify_label:
+            logits = torch.einsum('bchw,nc->bnhw', logits, text_feature_vecs[self.n_datasets])  # library GEMM (:692)
+            if self._matrices is None or self._matrices[0].device != logits.device:
+                self._matrices = [self.classRemapper.getRemapMatrix(i).to(logits.device)
+                                  for i in range(self.n_datasets)]
+            graphs = self._matrices
+        else:
+            graphs = [text_feature_vecs[i] for i in range(self.n_datasets)]
+        present = _present_rows(dataset_ids, self.n_datasets)
+        per_ds = ops.mds_proj_ohem_ce(logits, target, dataset_ids, graphs, float(self.CELoss.thresh),
+                                      self.CELoss.ignore_lb, cache=self._graph_cache, per_dataset=True)
+        return _sum_present(per_ds, present)
+
+
+class CrossDatasetsCELoss_GNN(nn.Module):
+    """:714-776 — prototype head, bipartite projection, bilinear up-sampling, plain cross-entropy per dataset (+ the
+    sparsity / max-entropy graph regularisers), summed over the datasets present."""
+
+    def __init__(self, configer=None):
+        super().__init__()
+        self.configer = configer
+        self.n_datasets = self.configer.get('n_datasets')
+        self.num_prototype = _cfg(configer, 'contrast', 'num_prototype')
+        self.temperature = _cfg(configer, 'contrast', 'temperature')
+        self.with_mulbn = _cfg(configer, 'contrast', 'with_mulbn')
+        self.reweight = _cfg(configer, 'loss', 'reweight')
+        self.ignore_index = _cfg(configer, 'loss', 'ignore_index', default=255)
+        self.with_unify_label = _cfg(configer, 'loss', 'with_unify_label')
+        self.with_spa = _cfg(configer, 'loss', 'with_spa', default=False)
+        self.spa_loss_weight = _cfg(configer, 'loss', 'spa_loss_weight', default=0.0)
+        self.with_max_enc = _cfg(configer, 'loss', 'with_max_enc', default=False)
+        self.max_enc_weight = _cfg(configer, 'loss', 'max_enc_weight', default=0.0)
+        self.n_cats = [configer.get('dataset' + str(i), 'n_cats') for i in range(1, self.n_datasets + 1)]
+        self.CELoss = torch.nn.CrossEntropyLoss(ignore_index=255)  # kept for introspection only
+        if self.with_max_enc:
+            self.MSE_loss = torch.nn.MSELoss()
+        self._graph_cache = ops.BipartiteGraphs()
+
+    def forward(self, preds, target, dataset_ids, is_warmup=False):
+        logits = preds['seg']
+        unify_prototype = preds['unify_prototype']
+        bi_graphs = preds['bi_graphs']
+        logits = torch.einsum('bchw,nc->bnhw', logits, unify_prototype)  # library GEMM (:747)
+        present = _present_rows(dataset_ids, self.n_datasets)
+        per_ds = ops.mds_proj_ce_mean(logits, target, dataset_ids, list(bi_graphs)[:self.n_datasets], ignore=255,
+                                      cache=self._graph_cache)
+        loss = _sum_present(per_ds, present)
+        for i in range(self.n_datasets):
+            if not present[i]:
+                continue
+            if self.with_spa:
+                loss = loss + self.spa_loss_weight * torch.pow(torch.norm(bi_graphs[i], p='fro'), 2)
+            if self.with_max_enc:
+                gi = bi_graphs[i]
+                loss = loss + self.max_enc_weight * self.MSE_loss(torch.max(gi, dim=1)[0],
+                                                                  torch.ones(gi.size(0), device=gi.device))
+        return loss
 
 
 class _GridSplitProjection(torch.autograd.Function):
@@ -109,8 +251,7 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
 
     # -- helpers ----------------------------------------------------------------------------------------------
     def _present(self, dataset_ids):
-        ids = torch.as_tensor(dataset_ids).reshape(-1).tolist()  # the one host read of this forward
-        return [[b for b, v in enumerate(ids) if int(v) == i] for i in range(self.n_datasets)]
+        return _present_rows(dataset_ids, self.n_datasets)
 
     def _fused_ce(self, logits, target, dataset_ids, graphs, which):
         return ops.mds_proj_ohem_ce(logits, target, dataset_ids, list(graphs), float(self.mdsOhemCELoss.thresh),
@@ -234,3 +375,11 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
         if adj_loss is not None:
             loss = loss + self.adj_loss_weight * adj_loss
         return loss, orth_loss, aux_loss, adj_loss
+
+
+UnifyPrototypeFunction = _GridSplitProjection  # the reference's name (:779)
+
+_NATIVE = ("CrossDatasetsCELoss", "CrossDatasetsCELoss_CLIP", "CrossDatasetsCELoss_GNN", "CrossDatasetsCELoss_AdvGNN",
+           "LabelToOneHot", "UnifyPrototypeFunction", "OhemCELoss", "MdsOhemCELoss", "MdsOhemNLLPlusLoss", "ClassRemap",
+           "ClassRemapOneHotLabel")
+__getattr__ = _reference.module_getattr("lib.loss.loss_cross_datasets", _NATIVE)

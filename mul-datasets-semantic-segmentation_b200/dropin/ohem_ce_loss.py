@@ -1,4 +1,4 @@
-"""Drop-in for lib/loss/ohem_ce_loss.py (OhemCELoss :12-34, MdsOhemCELoss :36-90).
+"""Drop-in for lib/loss/ohem_ce_loss.py (OhemCELoss :12-34, MdsOhemCELoss :36-90, MdsOhemNLLPlusLoss :92-146).
 
 Same constructors, same ``forward`` signatures, same attributes (`thresh` as a 0-dim fp32 tensor holding
 -log(p), `ignore_lb`); the arithmetic runs in libmdseg_b200.so.  Differences a caller can observe:
@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import _reference
 
 
 class OhemCELoss(nn.Module):
@@ -52,3 +53,31 @@ class MdsOhemCELoss(nn.Module):
         [B, C_uni, h, w] (loss_cross_datasets.py:1006-1007 + :1074 in one autograd node, no host sync)."""
         return ops.mds_proj_ohem_ce(logits_uni, labels, dataset_ids, list(bi_graphs), float(self.thresh),
                                     self.ignore_lb)
+
+
+class MdsOhemNLLPlusLoss(nn.Module):
+    """lib/loss/ohem_ce_loss.py:92-146 — the "softmax in the unified space, project PROBABILITIES, up-sample, -log"
+    variant (AdjNLLPlusLoss, lib/loss/loss_helper.py:647-668) under one OHEM selection over the batch.
+
+    forward(logits [B, C_uni, h, w], labels [B, H, W], bi_graphs (list of [C_ds_i, C_uni]), dataset_ids [B]).
+    The reference's loss vector holds the valid pixels only; here ignored pixels stay in with loss 0, which changes
+    neither the threshold set nor the top-n_min set (n_min = #valid // 16).  Unlike the reference, the labels are
+    not modified in place (loss_helper.py:662 writes 0 into a COPY made by boolean indexing there as well)."""
+
+    def __init__(self, configer, thresh, ignore_lb=255):
+        super().__init__()
+        self.configer = configer
+        self.n_datasets = self.configer.get('n_datasets')
+        self.thresh = -torch.log(torch.tensor(thresh, requires_grad=False, dtype=torch.float))
+        self.ignore_lb = ignore_lb
+        self._graph_cache = ops.BipartiteGraphs()
+
+    def forward(self, logits, labels, bi_graphs, dataset_ids):
+        graphs = list(bi_graphs)[:self.n_datasets]
+        return ops.mds_nll_plus(logits, labels, dataset_ids, graphs, float(self.thresh), self.ignore_lb,
+                                cache=self._graph_cache)
+
+
+# RecallCrossEntropy / FocalLoss / AdjNLLPlusLoss (re-exported by the reference module, :10) and anything else:
+# the reference's own definitions
+__getattr__ = _reference.module_getattr("lib.loss.ohem_ce_loss", ("OhemCELoss", "MdsOhemCELoss", "MdsOhemNLLPlusLoss"))

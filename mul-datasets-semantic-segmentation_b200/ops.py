@@ -536,7 +536,7 @@ class _MdsProjOhemCE(torch.autograd.Function):
     """MdsOhemCELoss(project -> upsample -> CE) of loss_cross_datasets.py:1006-1007,1074 in four kernels."""
 
     @staticmethod
-    def forward(ctx, logits_uni, labels, dataset_ids, thresh, ignore, cache, *graphs):
+    def forward(ctx, logits_uni, labels, dataset_ids, thresh, ignore, cache, per_dataset, *graphs):
         _require_cuda(logits_uni, labels)
         x = logits_uni
         if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
@@ -560,33 +560,35 @@ class _MdsProjOhemCE(torch.autograd.Function):
         ymax = torch.empty(B, h, w, dtype=torch.float32, device=dev)  # channel maximum of y: the softmax shift
         all_sparse = all(not tab.g[i].dense for i in range(len(Cs)))
         _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef)
-        src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, False, c_alloc=cmax,
+        n_seg = len(Cs) if per_dataset else 1
+        src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, per_dataset, c_alloc=cmax,
                          cmax=ymax, cmax_ready=all_sparse)
         P = B * H * W
         loss_px = torch.empty(P, dtype=torch.float32, device=dev)
         lse_px = torch.empty(P, dtype=torch.float32, device=dev)
-        st = _new_states(1, thresh, dev)
+        st = _new_states(n_seg, thresh, dev)
         N.call("mdseg_up_ce_fwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, int(ignore),
                _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(ef), _stream())
-        out = _select(loss_px, B, H * W, None, st, 1)
+        out = _select(loss_px, B, H * W, ids if per_dataset else None, st, n_seg)
         ctx.save_for_backward(x, labels, ids, y, loss_px, lse_px, st, *graphs)
-        ctx.meta = (int(ignore), cache, Cs, cmax, (h, w, H, W))
+        ctx.meta = (int(ignore), cache, Cs, cmax, (h, w, H, W), bool(per_dataset))
         ctx.states = st
-        return out[0]
+        ctx.mark_non_differentiable(st)
+        return (out if per_dataset else out[0]), st
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _grad_states=None):
         x, labels, ids, y, loss_px, lse_px, st, *graphs = ctx.saved_tensors
-        ignore, cache, Cs, cmax, (h, w, H, W) = ctx.meta
+        ignore, cache, Cs, cmax, (h, w, H, W), per_dataset = ctx.meta
         B, Cu = x.shape[:2]
         dev = x.device
-        g = _grad_scalar(grad_out)
-        tab, keep = cache.table(list(graphs))
         n = len(Cs)
+        g = _grad_scalar(grad_out, n if per_dataset else 1)
+        tab, keep = cache.table(list(graphs))
         scratch = torch.empty(1, dtype=torch.float32, device=dev)  # non-NULL cmax selects the TMA kernels
-        src = _src_table([y.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False, c_alloc=cmax, cmax=scratch,
+        src = _src_table([y.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, per_dataset, c_alloc=cmax, cmax=scratch,
                          cmax_ready=True)
-        want_dg = any(ctx.needs_input_grad[6 + i] for i in range(n))
+        want_dg = any(ctx.needs_input_grad[7 + i] for i in range(n))
         if not want_dg:
             # one call: softmax recompute + adjoint of the upsample + broadcast through G^T (fused when it applies)
             dx = None
@@ -597,7 +599,7 @@ class _MdsProjOhemCE(torch.autograd.Function):
                 N.call("mdseg_mds_bwd", C.byref(src), C.byref(tab), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h,
                        w, H, W, ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, _ptr(dx), _DT[x.dtype],
                        _ptr(ws), nbytes, _stream())
-            return (dx, None, None, None, None, None, *([None] * n))
+            return (dx, None, None, None, None, None, None, *([None] * n))
         if N.lib.mdseg_up_ce_bwd_direct_is_fused(C.byref(src), h, w, H, W):
             # the fused single-pass kernel with the identity in place of G^T: one gradient plane d loss / d y
             dyA, dyB = torch.empty_like(y), None  # only the first C_ds planes of an image are written — and read
@@ -638,15 +640,123 @@ class _MdsProjOhemCE(torch.autograd.Function):
                 N.call("mdseg_proj_bwd_graph", _ptr(x), _DT[x.dtype], _ptr(dyA), _ptr(dyB), cmax, C.byref(tab),
                        _ptr(ids), B, h, w, _ptr(dG), stride, _stream())
             for i in range(n):
+                if ctx.needs_input_grad[7 + i]:
+                    dgs[i] = dG[i, :Cs[i] * Cu].view(Cs[i], Cu).to(graphs[i].dtype)
+        return (dx, None, None, None, None, None, None, *dgs)
+
+
+def mds_proj_ohem_ce(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255, cache=None, per_dataset=False):
+    """CE(upsample(project(logits_uni, graph[dataset]))) under OHEM — no host sync.  One selection over all images
+    (0-dim result, MdsOhemCELoss) or, with `per_dataset`, one selection per dataset (vector [n_datasets], NaN for a
+    dataset without images: OhemCELoss per dataset, lib/loss/loss_cross_datasets.py:701-708)."""
+    return _MdsProjOhemCE.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
+                                bool(per_dataset), *graphs)[0]
+
+
+def mds_proj_ce_mean(logits_uni, labels, dataset_ids, graphs, ignore=255, cache=None):
+    """Per-dataset plain cross-entropy means, vector [n_datasets]: nn.CrossEntropyLoss(ignore_index)(upsample(project(
+    logits[ids == d], G_d)), labels[ids == d]) (lib/loss/loss_cross_datasets.py:341-345, :753-768).  Runs as the fused
+    OHEM loss with a threshold below every loss (every pixel selected, ignored ones contribute 0 and get no gradient)
+    and is rescaled from the mean over all pixels to the mean over the valid ones on the device."""
+    out, st = _MdsProjOhemCE.apply(logits_uni, labels, dataset_ids, -1.0, int(ignore), cache or _default_graphs, True,
+                                   *graphs)
+    counts = st.view(torch.int64).view(-1, STATE_BYTES // 8)
+    n_valid, n_px = counts[:, 0].to(torch.float32), counts[:, 2].to(torch.float32)
+    return out * (n_px / n_valid)
+
+
+# ---- f4: MdsOhemNLLPlusLoss (softmax -> project probabilities -> upsample -> -log, one OHEM selection) ------------
+class _MdsNLLPlus(torch.autograd.Function):
+    """AdjNLLPlusLoss (lib/loss/loss_helper.py:647-668) under the selection of MdsOhemNLLPlusLoss
+    (lib/loss/ohem_ce_loss.py:92-146).  The reference's loss vector holds the valid pixels only; here ignored pixels
+    stay in the vector with loss 0 — never above a positive threshold, and never inside the top n_min (= n_valid // 16)
+    unless every remaining candidate is 0 as well, which leaves the mean and the gradient unchanged."""
+
+    @staticmethod
+    def forward(ctx, logits_uni, labels, dataset_ids, thresh, ignore, cache, *graphs):
+        _require_cuda(logits_uni, labels)
+        x = logits_uni
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            x = x.float()
+        x = x.contiguous()
+        B, Cu, h, w = x.shape
+        labels = _labels(labels)
+        if labels.dim() != 3 or labels.shape[0] != B:
+            raise ValueError("labels must be [B, H, W]")
+        H, W = labels.shape[1:]
+        dev = x.device
+        tab, keep = cache.table(list(graphs))
+        if tab.C_uni != Cu:
+            raise ValueError(f"graphs have C_uni={tab.C_uni}, logits have {Cu}")
+        Cs = [g.shape[0] for g in graphs]
+        cmax = max(Cs)
+        ids = _ids32(dataset_ids, B, dev)
+        ef = err_flag(dev)
+        pred = torch.empty(B, Cu, h, w, dtype=torch.float32, device=dev)
+        N.call("mdseg_softmax_nchw", _ptr(x), _DT[x.dtype], B, Cu, h * w, _ptr(pred), _stream())
+        q = torch.empty(B, cmax, h, w, dtype=torch.float32, device=dev)
+        _proj_fwd(pred, tab, ids, B, h, w, q, cmax, None, ef)
+        src = _src_table([q.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, False, c_alloc=cmax)
+        loss_px = torch.empty(B * H * W, dtype=torch.float32, device=dev)
+        st = _new_states(1, thresh, dev)
+        N.call("mdseg_up_nll_fwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, int(ignore),
+               _ptr(loss_px), _ptr(st), _ptr(ef), _stream())
+        out = _select(loss_px, B, H * W, None, st, 1)
+        ctx.save_for_backward(pred, labels, ids, q, loss_px, st, *graphs)
+        ctx.meta = (int(ignore), cache, Cs, cmax, (h, w, H, W), x.dtype)
+        ctx.states = st
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pred, labels, ids, q, loss_px, st, *graphs = ctx.saved_tensors
+        ignore, cache, Cs, cmax, (h, w, H, W), xdt = ctx.meta
+        B, Cu = pred.shape[:2]
+        dev = pred.device
+        n = len(Cs)
+        g = _grad_scalar(grad_out)
+        tab, keep = cache.table(list(graphs))
+        src = _src_table([q.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False, c_alloc=cmax)
+        dq = torch.zeros_like(q)
+        dst = _src_table([dq.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False, c_alloc=cmax)
+        N.call("mdseg_up_nll_bwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, ignore,
+               _ptr(loss_px), _ptr(st), _ptr(g), 1.0, C.byref(dst), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dpred = torch.empty_like(pred)
+            if any(tab.g[i].dense for i in range(tab.n_datasets)):
+                nb = N.lib.mdseg_proj_bwd_tc_workspace_bytes(C.byref(tab), N.F32)
+                ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+                N.call("mdseg_proj_bwd_tc", _ptr(dq), None, cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dpred), N.F32,
+                       _ptr(ws), nb, _stream())
+            else:
+                N.call("mdseg_proj_bwd", _ptr(dq), None, cmax, C.byref(tab), _ptr(ids), B, h, w, _ptr(dpred), N.F32,
+                       _stream())
+            dx = dpred if xdt == torch.float32 else torch.empty(pred.shape, dtype=xdt, device=dev)
+            N.call("mdseg_softmax_bwd_nchw", _ptr(pred), _ptr(dpred), B, Cu, h * w, _ptr(dx), _DT[xdt], _stream())
+        dgs = [None] * n
+        if any(ctx.needs_input_grad[6 + i] for i in range(n)):
+            stride = cmax * Cu
+            dG = torch.zeros(n, stride, dtype=torch.float32, device=dev)
+            if any(tab.g[i].dense for i in range(tab.n_datasets)):
+                nb = N.lib.mdseg_proj_bwd_graph_tc_workspace_bytes(C.byref(tab), B, h, w)
+                ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+                N.call("mdseg_proj_bwd_graph_tc", _ptr(pred), N.F32, _ptr(dq), None, cmax, C.byref(tab), _ptr(ids), B, h,
+                       w, _ptr(dG), stride, _ptr(ws), nb, _stream())
+            else:
+                N.call("mdseg_proj_bwd_graph", _ptr(pred), N.F32, _ptr(dq), None, cmax, C.byref(tab), _ptr(ids), B, h, w,
+                       _ptr(dG), stride, _stream())
+            for i in range(n):
                 if ctx.needs_input_grad[6 + i]:
                     dgs[i] = dG[i, :Cs[i] * Cu].view(Cs[i], Cu).to(graphs[i].dtype)
         return (dx, None, None, None, None, None, *dgs)
 
 
-def mds_proj_ohem_ce(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255, cache=None):
-    """One OHEM selection over all images: CE(upsample(project(logits_uni, graph[dataset]))) — no host sync."""
-    return _MdsProjOhemCE.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
-                                *graphs)
+def mds_nll_plus(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255, cache=None):
+    """mean over the OHEM set of -log(upsample(G_d softmax(logits_uni)))[label]: MdsOhemNLLPlusLoss.forward
+    (lib/loss/ohem_ce_loss.py:104-146) for a whole multi-dataset batch, no host sync."""
+    return _MdsNLLPlus.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
+                             *graphs)
 
 
 # ---- a10: per-dataset aux heads (upsample + OhemCE, one selection per dataset) ---------------------------
@@ -710,10 +820,6 @@ def up_ohem_ce(srcs, labels, dataset_ids, thresh, ignore=255, seg_per_dataset=Tr
     """Per-dataset OhemCE(upsample(srcs[d][ids==d]), labels[ids==d]) as a vector [n_datasets]
     (seg_per_dataset) or one selection over all images ([1]).  srcs[d]: [B, C_d, h, w] over ALL images."""
     return _UpOhemCE.apply(labels, dataset_ids, float(thresh), int(ignore), bool(seg_per_dataset), *srcs)
-
-
-def states_of(loss_tensor_fn_ctx):
-    return read_states(loss_tensor_fn_ctx)
 
 
 # ---- a11: evaluator accumulation --------------------------------------------------------------------------

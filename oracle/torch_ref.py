@@ -167,3 +167,45 @@ def eval_preds(probs):
 def nearest_label(label, size):
     """evaluate.py:156-157."""
     return F.interpolate(label.float().unsqueeze(1), size=size, mode="nearest").squeeze(1).long()
+
+
+def adj_nll_plus(x, adj, lb, ignore=IGNORE):
+    """AdjNLLPlusLoss.forward with reduction='none', lib/loss/loss_helper.py:654-668: softmax over the unified
+    classes, projection of the PROBABILITIES, bilinear up-sampling, -log at the label class, valid pixels only."""
+    pred = torch.softmax(x.float(), dim=1)
+    probs = torch.einsum("bchw, nc -> bnhw", pred, adj.float())
+    probs = F.interpolate(probs, size=(lb.size(1), lb.size(2)), mode="bilinear", align_corners=True)
+    probs = -torch.log(probs)
+    keep = lb != ignore
+    lb = lb.clone()
+    lb[lb == ignore] = 0
+    loss = torch.gather(probs, 1, lb.long().unsqueeze(1)).squeeze(1)
+    return loss[keep]
+
+
+def mds_ohem_nll_plus_loss(logits, labels, bi_graphs, dataset_ids, n_datasets, thresh_p, ignore=IGNORE):
+    """MdsOhemNLLPlusLoss.forward, lib/loss/ohem_ce_loss.py:104-146."""
+    thresh = neg_log_thresh(thresh_p).to(labels.device)
+    n_min = labels[labels != ignore].numel() // 16
+    losses = []
+    for i in range(n_datasets):
+        if not (dataset_ids == i).any():
+            continue
+        losses.append(adj_nll_plus(logits[dataset_ids == i], bi_graphs[i], labels[dataset_ids == i], ignore).view(-1))
+    return ohem_select_mean(torch.cat(losses, dim=0), n_min, thresh)
+
+
+def cross_datasets_ce_mean(logits_uni, labels, dataset_ids, graphs, upsample_to_labels=True, ignore=IGNORE):
+    """Per-dataset plain CE of the projected (and up-sampled) logits, summed over the datasets present:
+    CrossDatasetsCELoss.forward (lib/loss/loss_cross_datasets.py:329-346, no up-sampling) and
+    CrossDatasetsCELoss_GNN.forward (:749-768, with it)."""
+    loss = None
+    for i in range(len(graphs)):
+        if not (dataset_ids == i).any():
+            continue
+        r = project(logits_uni[dataset_ids == i], graphs[i])
+        if upsample_to_labels:
+            r = upsample(r, labels.shape[1:])
+        ce = F.cross_entropy(r.float(), labels[dataset_ids == i].long(), ignore_index=ignore)
+        loss = ce if loss is None else loss + ce
+    return loss

