@@ -42,5 +42,6 @@ def max_over_ranks(value, device="cpu"):
 
 
 def whole_job_rate(units_per_rank, world_size, ms_per_step):
-    """units/s of the whole job under weak scaling: every rank processed `units_per_rank` per step."""
+    """units/s of the whole job: every rank processed `units_per_rank` per step (the workload's batch per rank under
+    weak scaling, its share of the batch under strong scaling)."""
     return units_per_rank * world_size / (ms_per_step * 1e-3)
