@@ -69,11 +69,14 @@ def parse():
                     help="onehot: 0/1 column-one-hot graphs (SEG stage, the headline).  dense: soft trainable graphs "
                          "softmax(randn * 4) with requires_grad (GNN stage): projection, adjoint and d bi_graph run on "
                          "the tcgen05 tensor cores; not the headline config")
-    ap.add_argument("--logits", default="randn", choices=["randn", "confident"],
+    ap.add_argument("--logits", default="randn", choices=["randn", "confident", "mixed"],
                     help="randn: SURVEY 8d's headline batch (every loss far above the threshold: threshold branch of the "
                          "OHEM selection).  confident: labels constant in blocks of 128 x 128 px and +12 on the unified "
                          "channels of the block's class, so fewer than n_min pixels are hard and the top-k fallback "
-                         "(radix select over all 33.5 M losses, ohem_ce_loss.py:87-88) runs and is timed")
+                         "(radix select over all 33.5 M losses, ohem_ce_loss.py:87-88) runs and is timed.  mixed: as "
+                         "confident, but the logits of every eighth block predict a wrong class: ~12 % of the pixels "
+                         "are hard (threshold branch) and whole regions carry no gradient, what a partly trained net "
+                         "looks like (the backward skips warps without a selected pixel)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's batch per GPU.  strong: the batch is split over the ranks "
                          "(SURVEY 8e: global batch 16 -> 2 images per GPU at N = 8)")
@@ -130,7 +133,7 @@ def make_batch(workload, device, seed, images=None, logits="randn"):
     pred = torch.empty(B, H, W, dtype=torch.int64, device=device)
     for b, d in enumerate(ids):
         pred[b] = torch.randint(0, n_cats[d], (H, W), generator=dgen, device=device)
-    if logits == "confident":
+    if logits in ("confident", "mixed"):
         # spatially coherent labels (blocks of 32 x 32 low-res cells) that the logits predict: raw id r -> class r % C
         blk = 32
         for b, d in enumerate(ids):
@@ -140,7 +143,12 @@ def make_batch(workload, device, seed, images=None, logits="randn"):
             fy, fx = H // h, W // w
             raw[b] = low.repeat_interleave(fy, 0).repeat_interleave(fx, 1)[:H, :W].to(torch.uint8)  # raw id == class
             col_cls = graphs[d].argmax(0).to(device)                                              # class of unified u
-            x[b] += 12.0 * (col_cls[:, None, None] == low[None]).to(x.dtype)
+            guess = low
+            if logits == "mixed":  # every eighth block is predicted wrongly
+                wrong = (torch.rand(cls.shape, generator=dgen, device=device) < 0.125)
+                wrong = wrong.repeat_interleave(blk, 0)[:h].repeat_interleave(blk, 1)[:, :w]
+                guess = torch.where(wrong, (low + 1) % c, low)
+            x[b] += 12.0 * (col_cls[:, None, None] == guess[None]).to(x.dtype)
             raw[b][torch.rand(H, W, generator=dgen, device=device) < 0.03] = 250                  # void -> 255
     return dict(n_cats=n_cats, c_uni=c_uni, ids=ids, h=h, w=w, H=H, W=W, x=x, raw=raw, pred=pred, graphs=graphs,
                 luts=luts)
@@ -206,8 +214,10 @@ def config_of(args, world):
         "workload": WORKLOAD_NAMES[args.workload], "name": args.workload, "pixels_per_step_per_gpu": px,
         "labels": args.label_dtype, "preds": args.pred_dtype,
         "logits": f"{args.logits_dtype} NCHW (CE arithmetic fp32)",
-        "logit_values": "randn (every loss above the OHEM threshold: threshold branch)" if args.logits == "randn" else
-                        "confident (block labels predicted by the logits: top-k fallback branch)",
+        "logit_values": {"randn": "randn (every loss above the OHEM threshold: threshold branch)",
+                         "confident": "confident (block labels predicted by the logits: top-k fallback branch)",
+                         "mixed": "mixed (block labels, every eighth block predicted wrongly: threshold branch, ~12 % "
+                                  "of the pixels selected)"}[args.logits],
         "bi_graphs": "0/1 column-one-hot (SEG stage)" if args.bi_graphs == "onehot" else
                      "dense fp32 softmax graphs with grad (GNN stage; tcgen05 projection, adjoint, d bi_graph)",
         "ohem_thresh": 0.4, "aux_heads": bool(args.with_aux),
@@ -227,7 +237,7 @@ KERNELS_PER_CALL = {"mdseg_up_ce_bwd_direct": 3, "mdseg_proj_fwd_tc": 2, "mdseg_
                     "mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
                     "mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
                     "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
-                    "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 2, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
+                    "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 3, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
 
 
 def run_ours(args, rank, world, local_rank):

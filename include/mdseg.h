@@ -481,6 +481,19 @@ int mdseg_up_nll_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset
                      const mdseg_ohem_state* states, const float* grad_out, float grad_scale,
                      const mdseg_src_table* dst /*host*/, void* stream);
 
+/* ---- f2: the prototype head for 16-bit features on TMA + tcgen05 --------------------------------------------
+ * out[b, n, p] = sum_k feats[b, k, p] * proto[n, k]: torch.einsum('bchw,nc->bnhw', feats, unify_prototype)
+ * (lib/models/semseg.py:325-333,342-343; lib/loss/loss_cross_datasets.py:950,961,971) under amp.autocast.
+ * feats: [n_images, K, hw] bf16 / fp16 (NCHW; hw % 8 == 0, 16-byte aligned).  proto_t: the prototypes converted to
+ * the feature dtype, row-major [n_tiles * NT, ldb] (ldb >= K, ldb % 8 == 0, columns >= K zero) with
+ * NT = mdseg_head_tc16_tile(N), rows >= N zero.  The same call gives d feats = dlogits x prototypes^T (K = the
+ * number of prototypes, proto_t = the transposed prototypes).
+ * out: [n_images, N, hw] fp32 or the feature dtype.  The features are read by TMA as MN-major UMMA operands — no
+ * thread touches them. */
+int mdseg_head_tc16_tile(int N);
+int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, int K, int64_t hw, const void* proto_t, int ldb,
+                        int N, void* out, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,10 @@ struct TcArgs {
   const float* dyB;                      // may be NULL
   void* dx;
   int nt;                                // unified channels per N tile, multiple of 16
+  // forward N tiling (blockIdx.z): dataset d's classes in n_tiles_f[d] tiles of nt_f[d] rows (multiple of 16, <= 256);
+  // one tile when C_ds <= 256 (the bipartite graphs), two or more for the prototype head (C_uni 358 classes)
+  int nt_f[MDSEG_MAX_DATASETS];
+  int n_tiles_f[MDSEG_MAX_DATASETS];
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,19 +169,20 @@ template <> struct Split<1> {
   }
 };
 
-// ---- prep: G_d [C_ds, C_uni] fp32 -> per K-chunk, per term, canonical K-major core-matrix layout ---------
-// chunk (d, kc) holds TERMS blocks of [Npad rows][32 k]: byte offset of (term t, row n, k) inside the chunk =
-// t * Npad * 64 + (k / 8) * (Npad * 16) + n * 16 + (k % 8) * 2.
+// ---- prep: G_d [C_ds, C_uni] fp32 -> per N tile, per K-chunk, per term, canonical K-major core-matrix layout ---------
+// chunk (d, z, kc) holds TERMS blocks of [nt rows][32 k]: byte offset of (term t, row r, k) inside the chunk =
+// t * nt * 64 + (k / 8) * (nt * 16) + r * 16 + (k % 8) * 2; row r of tile z is class z * nt + r.
 template <int TERMS>
 __global__ void __launch_bounds__(256) proj_tc_prep_kernel(const mdseg_graph_table tab, unsigned tc_mask, int n_chunks,
                                                            int fmt, unsigned char* gw, const TcArgs a) {
   const int d = blockIdx.y;
   if (!((tc_mask >> d) & 1u)) return;
   const mdseg_sparse_graph g = tab.g[d];
-  const int npad = pad16(g.C_ds);
-  const int groups = n_chunks * 4 * npad;  // (chunk, k-group of 8, row)
+  const int npad = a.nt_f[d];
+  const int groups = a.n_tiles_f[d] * n_chunks * 4 * npad;  // (tile, chunk, k-group of 8, row)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += gridDim.x * blockDim.x) {
-    const int n = i % npad, kg = (i / npad) % 4, kc = i / (4 * npad);
+    const int r = i % npad, kg = (i / npad) % 4, kc = (i / (4 * npad)) % n_chunks, z = i / (4 * npad * n_chunks);
+    const int n = z * npad + r;
     uint32_t w[TERMS][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -192,10 +197,10 @@ __global__ void __launch_bounds__(256) proj_tc_prep_kernel(const mdseg_graph_tab
 #pragma unroll
       for (int t = 0; t < TERMS; ++t) w[t][j] = o[t];
     }
-    unsigned char* chunk = gw + a.g_off[d] + (int64_t)kc * TERMS * npad * 64;
+    unsigned char* chunk = gw + a.g_off[d] + ((int64_t)z * n_chunks + kc) * TERMS * npad * 64;
 #pragma unroll
     for (int t = 0; t < TERMS; ++t)
-      *reinterpret_cast<uint4*>(chunk + (int64_t)t * npad * 64 + kg * (npad * 16) + n * 16) =
+      *reinterpret_cast<uint4*>(chunk + (int64_t)t * npad * 64 + kg * (npad * 16) + r * 16) =
           make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
   }
 }
@@ -252,9 +257,11 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 4 : 2) proj_tc_kernel(const
   const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
   if (d < 0 || d >= a.n_datasets || !((a.tc_mask >> d) & 1u)) return;  // uniform per CTA
   const int C_ds = a.C_ds[d];
-  const int u0 = kBwd ? (int)blockIdx.z * a.nt : 0;                      // first output channel of this N tile
-  const int n_out = kBwd ? ((a.C_uni - u0) < a.nt ? (a.C_uni - u0) : a.nt) : C_ds;  // valid output channels
-  const int npad = kBwd ? a.nt : pad16(C_ds);
+  if (!kBwd && (int)blockIdx.z >= a.n_tiles_f[d]) return;                // uniform per CTA
+  const int npad = kBwd ? a.nt : a.nt_f[d];
+  const int u0 = (int)blockIdx.z * npad;                                 // first output channel of this N tile
+  const int n_all = kBwd ? a.C_uni : C_ds;
+  const int n_out = (n_all - u0) < npad ? (n_all - u0) : npad;           // valid output channels
   const int K = kBwd ? C_ds : a.C_uni;
   const int n_chunks = (K + kKB - 1) / kKB;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 4 : 2) proj_tc_kernel(const
   const float* dA = kBwd ? a.dyA + (long long)b * a.y_cmax * a.hw : nullptr;
   const float* dB = (kBwd && a.dyB) ? a.dyB + (long long)b * a.y_cmax * a.hw : nullptr;
   const uint32_t b_chunk_bytes = (uint32_t)(TERMS * npad * 64);
-  const unsigned char* gchunks = a.gw + a.g_off[d] + (kBwd ? (size_t)blockIdx.z * n_chunks * b_chunk_bytes : 0);
+  const unsigned char* gchunks = a.gw + a.g_off[d] + (size_t)blockIdx.z * n_chunks * b_chunk_bytes;
   const uint32_t idesc = umma_idesc(a.fmt, npad);
 
   // this thread's 16 channels of a chunk, one chunk ahead in registers so that the HBM latency of chunk kc + 1
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 4 : 2) proj_tc_kernel(const
   // quarter take alternate groups of 16 columns
   bar_wait(&bar_acc, 0);
   tc_fence_after();
-  float* yb = kBwd ? nullptr : a.y + (long long)b * a.y_cmax * a.hw;
+  float* yb = kBwd ? nullptr : a.y + ((long long)b * a.y_cmax + u0) * a.hw;
   T* dxb = kBwd ? (T*)a.dx + ((long long)b * a.C_uni + u0) * a.hw : nullptr;
   for (int n0 = (warp >> 2) * 16; n0 < npad; n0 += 32) {
     float acc[16];
@@ -388,8 +395,15 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 4 : 2) proj_tc_kernel(const
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+constexpr int kMaxClasses = 1024;  // forward: up to four N tiles of 256
+
 bool tc_dataset(const mdseg_sparse_graph& g, int C_uni) {
-  return g.dense != nullptr && g.C_ds >= 8 && g.C_ds <= kMaxN && C_uni >= 32;
+  return g.dense != nullptr && g.C_ds >= 8 && g.C_ds <= kMaxClasses && C_uni >= 32;
+}
+// forward N tiling of C_ds classes: equal tiles of at most kMaxN rows
+void fwd_tiling(int C_ds, int* n_tiles, int* nt) {
+  *n_tiles = (pad16(C_ds) + kMaxN - 1) / kMaxN;
+  *nt = pad16((C_ds + *n_tiles - 1) / *n_tiles);
 }
 int terms_of(int dtype) { return dtype == MDSEG_F32 ? 3 : 1; }
 
@@ -402,8 +416,11 @@ extern "C" size_t mdseg_proj_fwd_tc_workspace_bytes(const mdseg_graph_table* gra
   const int n_chunks = (graphs->C_uni + kKB - 1) / kKB;
   size_t total = 256;
   for (int i = 0; i < graphs->n_datasets; ++i)
-    if (tc_dataset(graphs->g[i], graphs->C_uni))
-      total += (size_t)n_chunks * terms_of(dtype) * pad16(graphs->g[i].C_ds) * 64;
+    if (tc_dataset(graphs->g[i], graphs->C_uni)) {
+      int n_tiles, nt;
+      fwd_tiling(graphs->g[i].C_ds, &n_tiles, &nt);
+      total += (size_t)n_tiles * n_chunks * terms_of(dtype) * nt * 64;
+    }
   return total;
 }
 
@@ -431,18 +448,22 @@ extern "C" int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_tab
   a.dyA = nullptr; a.dyB = nullptr; a.dx = nullptr; a.nt = 0;
   const int terms = terms_of(dtype);
   a.tc_mask = 0;
-  int npad_max = 0;
+  int npad_max = 0, tiles_max = 1, groups_max = 0;
   long long off = 0;
   for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
-    a.g_off[i] = 0; a.C_ds[i] = 0;
+    a.g_off[i] = 0; a.C_ds[i] = 0; a.nt_f[i] = 0; a.n_tiles_f[i] = 0;
     if (i >= graphs->n_datasets) continue;
     a.C_ds[i] = graphs->g[i].C_ds;
     if (!tc_dataset(graphs->g[i], graphs->C_uni)) continue;
     MDSEG_REQUIRE(y_cmax >= graphs->g[i].C_ds, "mdseg_proj_fwd_tc: y_cmax %d < C_ds %d", y_cmax, graphs->g[i].C_ds);
     a.tc_mask |= 1u << i;
     a.g_off[i] = off;
-    off += (long long)a.n_chunks * terms * pad16(graphs->g[i].C_ds) * 64;
-    npad_max = pad16(graphs->g[i].C_ds) > npad_max ? pad16(graphs->g[i].C_ds) : npad_max;
+    fwd_tiling(graphs->g[i].C_ds, &a.n_tiles_f[i], &a.nt_f[i]);
+    off += (long long)a.n_tiles_f[i] * a.n_chunks * terms * a.nt_f[i] * 64;
+    npad_max = a.nt_f[i] > npad_max ? a.nt_f[i] : npad_max;
+    tiles_max = a.n_tiles_f[i] > tiles_max ? a.n_tiles_f[i] : tiles_max;
+    const int groups = a.n_tiles_f[i] * a.n_chunks * 4 * a.nt_f[i];
+    groups_max = groups > groups_max ? groups : groups_max;
   }
   // sparse graphs and dense ones outside the tensor-core envelope: the CSR / FFMA kernels of proj.cu
   if (int rc = proj_fwd_rest(x, dtype, graphs, dataset_ids, n_images, h, w, y, y_cmax, cmax_out, err_flag, a.tc_mask, s))
@@ -452,8 +473,8 @@ extern "C" int mdseg_proj_fwd_tc(const void* x, int dtype, const mdseg_graph_tab
   a.a_stage_bytes = terms * 4 * kTM * 16;
   a.b_stage_bytes = terms * npad_max * 64;
   const size_t smem = (size_t)kStagesTc * (a.a_stage_bytes + a.b_stage_bytes);
-  const dim3 pgrid((unsigned)((a.n_chunks * 4 * npad_max + 255) / 256), (unsigned)graphs->n_datasets);
-  const dim3 grid((unsigned)((a.hw + kTM - 1) / kTM), (unsigned)n_images);
+  const dim3 pgrid((unsigned)((groups_max + 255) / 256), (unsigned)graphs->n_datasets);
+  const dim3 grid((unsigned)((a.hw + kTM - 1) / kTM), (unsigned)n_images, (unsigned)tiles_max);
 #define MDSEG_TC_LAUNCH(T, TERMS)                                                                                  \
   do {                                                                                                             \
     proj_tc_prep_kernel<TERMS><<<pgrid, 256, 0, s>>>(*graphs, a.tc_mask, a.n_chunks, a.fmt,                        \
@@ -528,7 +549,7 @@ extern "C" int mdseg_proj_bwd_tc(const float* dyA, const float* dyB, int y_cmax,
   long long off = 0;
   int max_groups = 0;
   for (int i = 0; i < MDSEG_MAX_DATASETS; ++i) {
-    a.g_off[i] = 0; a.C_ds[i] = 0;
+    a.g_off[i] = 0; a.C_ds[i] = 0; a.nt_f[i] = 0; a.n_tiles_f[i] = 0;
     if (i >= graphs->n_datasets) continue;
     a.C_ds[i] = graphs->g[i].C_ds;
     if (!tc_dataset(graphs->g[i], graphs->C_uni)) continue;
@@ -589,10 +610,11 @@ struct DgArgs {
   const float* dyA;
   const float* dyB;
   const int32_t* dataset_ids;
-  float* part;                 // [n_images][2 M tiles][n_slabs][128][npad]
+  float* part;                 // [n_images][n_mt M tiles][n_nt N tiles][n_slabs][128][npad]
   int C_ds[MDSEG_MAX_DATASETS];
   unsigned tc_mask;
-  int n_datasets, C_uni, npad, y_cmax;
+  int n_datasets, C_uni, npad, y_cmax;  // npad: width of one N tile of unified channels (multiple of 16, <= 384)
+  int n_mt, n_nt;              // M tiles of 128 classes (grid), N tiles of npad unified channels
   long long hw, slab;
   int n_slabs, fmt;
   int a_stage_bytes, b_stage_bytes;
@@ -605,13 +627,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) proj_tc_dgraph_kernel(const __g
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_s;
 
-  const int b = blockIdx.z, mt = blockIdx.y, sl = blockIdx.x;
+  const int b = blockIdx.z, mt = (int)blockIdx.y % a.n_mt, nz = (int)blockIdx.y / a.n_mt, sl = blockIdx.x;
   const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
   if (d < 0 || d >= a.n_datasets || !((a.tc_mask >> d) & 1u)) return;
   const int C_ds = a.C_ds[d];
   const int n0 = mt * kDgM;
   if (n0 >= C_ds) return;
   const int npad = a.npad;
+  const int c0x = nz * npad;   // first unified channel of this N tile
   const int R = kDgM + npad;  // rows staged per chunk: 128 of dy, npad of x
   const int tid = threadIdx.x, warp = tid >> 5;
   const long long p_beg = (long long)sl * a.slab;
@@ -659,7 +682,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) proj_tc_dgraph_kernel(const __g
         if (n0 + r < C_ds) { kind[j] = 1; srcA[j] = dA + (long long)(n0 + r) * a.hw + p_beg + kg * 8; }
       } else {
         dst_off[j] = a.a_stage_bytes * kStagesTc + kg * (npad * 16) + (r - kDgM) * 16;  // relative to sA of stage 0 ...
-        if (r - kDgM < a.C_uni) { kind[j] = 2; srcX[j] = xb + (long long)(r - kDgM) * a.hw + p_beg + kg * 8; }
+        if (c0x + r - kDgM < a.C_uni) { kind[j] = 2; srcX[j] = xb + (long long)(c0x + r - kDgM) * a.hw + p_beg + kg * 8; }
       }
     }
   }
@@ -775,7 +798,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) proj_tc_dgraph_kernel(const __g
   // epilogue: TMEM lane = class row of the M tile, columns = unified channels -> this CTA's slot of the workspace
   bar_wait(&bar_acc, 0);
   tc_fence_after();
-  float* slot = a.part + (((long long)b * 2 + mt) * a.n_slabs + sl) * (long long)kDgM * npad;
+  float* slot = a.part + ((((long long)b * a.n_mt + mt) * a.n_nt + nz) * a.n_slabs + sl) * (long long)kDgM * npad;
   const int row = (warp & 3) * 32 + (tid & 31);
   for (int c0 = (warp >> 2) * 16; c0 < npad; c0 += 32) {
     float acc[16];
@@ -799,16 +822,32 @@ __global__ void __launch_bounds__(256) proj_tc_dgraph_reduce_kernel(const DgArgs
   if (idx >= C_ds * a.C_uni) return;
   const int n = idx / a.C_uni, c = idx - n * a.C_uni;
   const int mt = n / kDgM, r = n - mt * kDgM;
+  const int nz = c / a.npad, cc = c - nz * a.npad;
   float sum = 0.f;
   for (int b = 0; b < n_images; ++b) {
     if ((a.dataset_ids ? a.dataset_ids[b] : 0) != d) continue;
-    const float* base = a.part + (((long long)b * 2 + mt) * a.n_slabs) * (long long)kDgM * a.npad + (long long)r * a.npad + c;
+    const float* base = a.part + ((((long long)b * a.n_mt + mt) * a.n_nt + nz) * a.n_slabs) * (long long)kDgM * a.npad +
+                        (long long)r * a.npad + cc;
     for (int sl = 0; sl < a.n_slabs; ++sl) sum += base[(long long)sl * kDgM * a.npad];
   }
   dG[(long long)d * dg_stride + idx] += sum;
 }
 
-bool dg_dataset(const mdseg_sparse_graph& g, int C_uni) { return tc_dataset(g, C_uni) && pad16(C_uni) <= kDgMaxN; }
+bool dg_dataset(const mdseg_sparse_graph& g, int C_uni) { return tc_dataset(g, C_uni) && C_uni <= 4 * kDgMaxN; }
+// N tiling of the unified channels: equal tiles of at most kDgMaxN
+void dg_tiling(int C_uni, int* n_nt, int* npad) {
+  *n_nt = (pad16(C_uni) + kDgMaxN - 1) / kDgMaxN;
+  *npad = pad16((C_uni + *n_nt - 1) / *n_nt);
+}
+int dg_m_tiles(const mdseg_graph_table* graphs) {
+  int m = 1;
+  for (int i = 0; i < graphs->n_datasets; ++i)
+    if (dg_dataset(graphs->g[i], graphs->C_uni)) {
+      const int t = (graphs->g[i].C_ds + kDgM - 1) / kDgM;
+      m = t > m ? t : m;
+    }
+  return m;
+}
 
 int dg_slabs(int n_images, long long hw) {
   long long n = (2LL * sm_count() + n_images - 1) / n_images;  // about two CTAs' worth of work per SM
@@ -825,7 +864,9 @@ extern "C" size_t mdseg_proj_bwd_graph_tc_workspace_bytes(const mdseg_graph_tabl
   using namespace mdseg;
   if (!graphs || graphs->C_uni <= 0 || n_images <= 0 || h <= 0 || w <= 0) return 256;
   const int n_slabs = dg_slabs(n_images, (long long)h * w);
-  return (size_t)n_images * 2 * n_slabs * kDgM * pad16(graphs->C_uni) * 4 + 512;
+  int n_nt, npad;
+  dg_tiling(graphs->C_uni, &n_nt, &npad);
+  return (size_t)n_images * dg_m_tiles(graphs) * n_nt * n_slabs * kDgM * npad * 4 + 512;
 }
 
 extern "C" int mdseg_proj_bwd_graph_tc(const void* x, int dtype, const float* dyA, const float* dyB, int y_cmax,
@@ -846,7 +887,9 @@ extern "C" int mdseg_proj_bwd_graph_tc(const void* x, int dtype, const float* dy
   DgArgs a;
   a.x = x; a.dyA = dyA; a.dyB = dyB; a.dataset_ids = dataset_ids;
   a.part = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  a.n_datasets = graphs->n_datasets; a.C_uni = graphs->C_uni; a.npad = pad16(graphs->C_uni); a.y_cmax = y_cmax;
+  a.n_datasets = graphs->n_datasets; a.C_uni = graphs->C_uni; a.y_cmax = y_cmax;
+  dg_tiling(graphs->C_uni, &a.n_nt, &a.npad);
+  a.n_mt = dg_m_tiles(graphs);
   a.hw = (long long)h * w;
   a.n_slabs = dg_slabs(n_images, a.hw);
   a.slab = ((a.hw + a.n_slabs - 1) / a.n_slabs + kKB - 1) / kKB * kKB;  // whole chunks, 32-pixel aligned starts
@@ -873,7 +916,7 @@ extern "C" int mdseg_proj_bwd_graph_tc(const void* x, int dtype, const float* dy
   a.b_stage_bytes = terms * 4 * a.npad * 16;
   const size_t smem = (size_t)kStagesTc * (a.a_stage_bytes + a.b_stage_bytes);
   MDSEG_REQUIRE(smem <= 220 * 1024, "mdseg_proj_bwd_graph_tc: C_uni too large for the staged operands");
-  const dim3 grid((unsigned)a.n_slabs, 2u, (unsigned)n_images);
+  const dim3 grid((unsigned)a.n_slabs, (unsigned)(a.n_mt * a.n_nt), (unsigned)n_images);
   const dim3 rgrid((unsigned)(((long long)cmax * a.C_uni + 255) / 256), (unsigned)graphs->n_datasets);
 #define MDSEG_DG_LAUNCH(T, TERMS)                                                                       \
   do {                                                                                                  \

@@ -197,7 +197,7 @@ def target_bipart_from_hist(hist, bipart_graph, ignore_index=255):
 def eval_find_use_and_unuse_label(configer, net, dls=None):
     """evaluate.py:1788-1930 — per dataset the rectangular ``[n_cats, C_uni]`` histogram of the labels against the
     arg-max of the UNIFIED logits (prototype einsum -> bilinear up-sampling -> soft-max -> arg-max), then the
-    bucket rules that produce ``target_bi_graph`` for the GNN stage.  The einsum is the reference's own library GEMM;
+    bucket rules that produce ``target_bi_graph`` for the GNN stage.  The prototype einsum runs on tcgen05 (ops.prototype_head);
     up-sampling + arg-max (soft-max is monotone, no [C_uni, H, W] tensor) and the histogram run in libmdseg_b200.so.
     `dls` defaults to the reference's ``get_data_loader(configer, aux_mode='train', distributed=..., stage=2)``."""
     org_aux = net.aux_mode
@@ -220,7 +220,7 @@ def eval_find_use_and_unuse_label(configer, net, dls=None):
             label = label.squeeze(1).to(dev, non_blocking=True)
             H, W = label.shape[-2:]
             emb = net(imgs.to(dev), dataset=i)
-            logits = torch.einsum('bchw,nc->bnhw', emb['seg'], unify_prototype.to(dev))
+            logits = ops.prototype_head(emb['seg'], unify_prototype.to(dev))  # semseg.py:342-343 on tcgen05
             for b in range(label.shape[0]):
                 pred = ops.eval_fused([(logits[b], False)], (H, W))[0]
                 ops.confusion(label[b], pred, n_classes, total_cats, ignore=255, hist=hist)

@@ -15,8 +15,9 @@ What runs where:
         by ``max_rate`` (:1063-1071), with gradients to the logits AND to every ``bi_graphs[i]`` (tcgen05 split-K
         ``d bi_graph``); aux heads from the dataset prototypes (:941-951, :1044-1048) through the fused
         up-sample + OhemCE(0.7) kernels;
-  * the prototype contractions ``einsum('bchw,nc->bnhw', feats, unify_prototype[...])`` (:950, :961, :971) are plain
-    library GEMMs and stay ``torch.einsum`` (cuBLAS), exactly the reference's call;
+  * the prototype contractions ``einsum('bchw,nc->bnhw', feats, unify_prototype[...])`` (:950, :961, :971) — the
+    producer of the unified logits, SURVEY §8 f2 — run on the tcgen05 tensor cores (``ops.prototype_head``: forward,
+    d feats and the split-K d prototype); only the GridSplit variant (:779-809) keeps the library einsum;
   * the graph regularisers (orth / spa / max-enc / adj MSE, init-stage graph and prototype MSE, adversarial BCE /
     MSE terms) act on ``[C_ds, C_uni]``-sized tensors; they are restated with the same torch ops.
 
@@ -122,7 +123,7 @@ class CrossDatasetsCELoss_CLIP(nn.Module):
         logits = preds['seg']
         text_feature_vecs = preds['prototypes']
         if self.with_unify_label:
-            logits = torch.einsum('bchw,nc->bnhw', logits, text_feature_vecs[self.n_datasets])  # library GEMM (:692)
+            logits = ops.prototype_head(logits, text_feature_vecs[self.n_datasets])  # :692 on tcgen05
             if self._matrices is None or self._matrices[0].device != logits.device:
                 self._matrices = [self.classRemapper.getRemapMatrix(i).to(logits.device)
                                   for i in range(self.n_datasets)]
@@ -163,7 +164,7 @@ class CrossDatasetsCELoss_GNN(nn.Module):
         logits = preds['seg']
         unify_prototype = preds['unify_prototype']
         bi_graphs = preds['bi_graphs']
-        logits = torch.einsum('bchw,nc->bnhw', logits, unify_prototype)  # library GEMM (:747)
+        logits = ops.prototype_head(logits, unify_prototype)  # :747 on tcgen05
         present = _present_rows(dataset_ids, self.n_datasets)
         per_ds = ops.mds_proj_ce_mean(logits, target, dataset_ids, list(bi_graphs)[:self.n_datasets], ignore=255,
                                       cache=self._graph_cache)
@@ -272,7 +273,7 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
         loss = orth_loss = aux_loss = adj_loss = None
         add = lambda acc, v: v if acc is None else acc + v
 
-        # ---- prototype head (:941-972): library GEMMs, as in the reference ----
+        # ---- prototype head (:941-972): tcgen05 GEMMs (ops.prototype_head) ----
         proto_aux = None
         if unify_prototype is not None and not init_gnn_stage:
             feats = logits
@@ -283,15 +284,15 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
                     if index_of[i] is None:
                         proto_aux.append(None)
                     else:  # low resolution; the up-sampling is fused into the loss kernel below
-                        proto_aux.append(torch.einsum('bchw,nc->bnhw', feats.index_select(0, index_of[i]),
-                                                      unify_prototype[cur:cur + self.n_cats[i]]))
+                        proto_aux.append(ops.prototype_head(feats.index_select(0, index_of[i]),
+                                                            unify_prototype[cur:cur + self.n_cats[i]]))
                     cur += self.n_cats[i]
                 head = unify_prototype[self.total_cats:]
             if self.GridSpilt:
                 self.M = self.M.to(dev)
                 logits = _GridSplitProjection.apply(feats, head, torch.as_tensor(dataset_ids).to(dev), self.M)
             else:
-                logits = torch.einsum('bchw,nc->bnhw', feats, head)
+                logits = ops.prototype_head(feats, head)
 
         if is_adv and self.with_orth:  # :977-982
             orth_loss = self.orth_weight * self.similarity_dsb(

@@ -531,6 +531,102 @@ def _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef):
                _ptr(ef), _stream())
 
 
+# ---- f2: the prototype head (producer of the unified logits) on the tcgen05 tensor cores ---------------------------
+def _dense_table(weight):
+    """GraphTable holding one dense matrix [n_rows, K] (no host copy, no density test)."""
+    tab = N.GraphTable()
+    tab.n_datasets = 1
+    tab.C_uni = weight.shape[1]
+    tab.g[0].C_ds, tab.g[0].nnz = weight.shape[0], weight.shape[0] * weight.shape[1]
+    tab.g[0].dense = weight.data_ptr()
+    return tab
+
+
+def _tc16_ok(x):
+    return x.dtype in (torch.bfloat16, torch.float16) and (x.shape[2] * x.shape[3]) % 8 == 0 and x.data_ptr() % 16 == 0
+
+
+def _head_tc16(a, wgt, out):
+    """out[b, n, p] = sum_k a[b, k, p] * wgt[n, k] with 16-bit `a` [B, K, h, w]; wgt: fp32 [n_rows, K] (any strides);
+    out: fp32 or a's dtype.  mdseg_head_fwd_tc16 (TMA + tcgen05)."""
+    B, K, h, w = a.shape
+    n_rows = wgt.shape[0]
+    nt = N.lib.mdseg_head_tc16_tile(n_rows)
+    ldb = (K + 7) // 8 * 8
+    wt = torch.zeros(((n_rows + nt - 1) // nt) * nt, ldb, dtype=a.dtype, device=a.device)
+    wt[:n_rows, :K] = wgt.to(a.dtype)
+    N.call("mdseg_head_fwd_tc16", _ptr(a), _DT[a.dtype], B, K, h * w, _ptr(wt), ldb, n_rows, _ptr(out), _DT[out.dtype],
+           _stream())
+
+
+class _PrototypeHead(torch.autograd.Function):
+    """logits[b, n, y, x] = sum_c feats[b, c, y, x] * proto[n, c]: torch.einsum('bchw,nc->bnhw', feats, unify_prototype)
+    of lib/models/semseg.py:325-333,342-343 and lib/loss/loss_cross_datasets.py:950,961,971 as a
+    [128 px, N] x [N, K] tcgen05 GEMM per CTA (mdseg_proj_fwd_tc with the prototypes in the role of the dense graph,
+    N tiled by 256).  Backward: d feats = proto^T dlogits (mdseg_proj_bwd_tc), d proto = dlogits feats^T as a split-K
+    GEMM over the pixels (mdseg_proj_bwd_graph_tc).  fp32 inputs: three bf16 terms per operand (1e-5 bar);
+    bf16 / fp16 inputs: one product in their own type, like autocast.  Output fp32."""
+
+    @staticmethod
+    def forward(ctx, feats, proto):
+        _require_cuda(feats, proto)
+        x = feats
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            x = x.float()
+        x = x.contiguous()
+        B, K, h, w = x.shape
+        if proto.dim() != 2 or proto.shape[1] != K:
+            raise ValueError(f"prototypes must be [N, {K}]")
+        wgt = proto.detach().to(torch.float32).contiguous()
+        Nn = wgt.shape[0]
+        y = torch.empty(B, Nn, h, w, dtype=torch.float32, device=x.device)
+        ctx.save_for_backward(x, wgt)
+        ctx.proto_dtype = proto.dtype
+        if _tc16_ok(x):
+            # 16-bit features: TMA-fed MN-major operands, warp-specialised (csrc/head_tc16.cu)
+            _head_tc16(x, wgt, y)
+            return y
+        tab = _dense_table(wgt)
+        nbytes = N.lib.mdseg_proj_fwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        N.call("mdseg_proj_fwd_tc", _ptr(x), _DT[x.dtype], C.byref(tab), None, B, h, w, _ptr(y), Nn, None, _ptr(ws),
+               nbytes, _ptr(err_flag(x.device)), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wgt = ctx.saved_tensors
+        B, K, h, w = x.shape
+        Nn = wgt.shape[0]
+        dy = dy.to(torch.float32).contiguous()
+        tab = _dense_table(wgt)
+        dx = dw = None
+        if ctx.needs_input_grad[0] and _tc16_ok(x):
+            # d feats = dlogits x prototypes^T: the same TMA-fed kernel with the transposed prototypes.  The incoming
+            # gradient is rounded to the feature dtype first (what the reference's autocast backward does to it)
+            dx = torch.empty_like(x)
+            _head_tc16(dy.to(x.dtype), wgt.t(), dx)
+        elif ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            nb = N.lib.mdseg_proj_bwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
+            ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+            N.call("mdseg_proj_bwd_tc", _ptr(dy), None, Nn, C.byref(tab), None, B, h, w, _ptr(dx), _DT[x.dtype], _ptr(ws),
+                   nb, _stream())
+        if ctx.needs_input_grad[1]:
+            dG = torch.zeros(1, Nn * K, dtype=torch.float32, device=x.device)
+            nb = N.lib.mdseg_proj_bwd_graph_tc_workspace_bytes(C.byref(tab), B, h, w)
+            ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+            N.call("mdseg_proj_bwd_graph_tc", _ptr(x), _DT[x.dtype], _ptr(dy), None, Nn, C.byref(tab), None, B, h, w,
+                   _ptr(dG), Nn * K, _ptr(ws), nb, _stream())
+            dw = dG.view(Nn, K).to(ctx.proto_dtype)
+        return dx, dw
+
+
+def prototype_head(feats, proto):
+    """einsum('bchw,nc->bnhw', feats [B, K, h, w], proto [N, K]) -> fp32 [B, N, h, w] on the tensor cores."""
+    return _PrototypeHead.apply(feats, proto)
+
+
 # ---- a5+a6+a7+a8+a9: the fused multi-dataset loss ------------------------------------------------------
 class _MdsProjOhemCE(torch.autograd.Function):
     """MdsOhemCELoss(project -> upsample -> CE) of loss_cross_datasets.py:1006-1007,1074 in four kernels."""
