@@ -494,6 +494,17 @@ int mdseg_head_tc16_tile(int N);
 int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, int K, int64_t hw, const void* proto_t, int ldb,
                         int N, void* out, int out_dtype, void* stream);
 
+/* ---- MscEvalCrop (evaluate.py:650-753): sliding-window evaluation ------------------------------------------
+ * probs[c, y0 + y, x0 + x] += g(softmax_c(logits)[c, y, x] (+ softmax_c(logits_flip)[c, y, cw - 1 - x])) for one chip
+ * [C, ch, cw] inside the scale-level map probs [C, PH, PW] (fp32).  logits_flip may be NULL; exp_after != 0 applies
+ * exp() to the summed probabilities, as the reference does when flip is on (evaluate.py:689). */
+int mdseg_eval_chip_accum(const void* logits, const void* logits_flip, int dtype, int C, int ch, int cw, float* probs,
+                          int PH, int PW, int y0, int x0, int exp_after, void* stream);
+/* dst[c] (+)= F.interpolate(src[c, y0:y0+sh, x0:x0+sw], (H, W), bilinear, align_corners=True)  (evaluate.py:722-724);
+ * first != 0 overwrites dst. */
+int mdseg_prob_resize_accum(const float* src, int C, int PH, int PW, int y0, int x0, int sh, int sw, float* dst, int H,
+                            int W, int first, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

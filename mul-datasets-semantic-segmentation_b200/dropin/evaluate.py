@@ -90,6 +90,70 @@ class MscEvalV0:
         return acc.miou()
 
 
+class MscEvalCrop:
+    """evaluate.py:650-753 — sliding-window multi-scale evaluator (upstream BiSeNet's cropped evaluation):
+    ``MscEvalCrop(cropsize, cropstride, flip, scales, lb_ignore)(net, dl, n_classes) -> float``.  The net returns
+    full-resolution logits (``net(crop)[0]``).  Per chip the soft-max(es), the reference's ``exp`` of the flipped sum
+    (:689, kept) and the add into the scale-level map are one kernel; per scale the bilinear resize of that map to
+    the label size and the add into the image-level map another; arg-max + int64 confusion matrix + one all-reduce
+    as in the other evaluators."""
+
+    def __init__(self, cropsize=1024, cropstride=2. / 3, flip=True, scales=(0.5, 0.75, 1, 1.25, 1.5, 1.75), lb_ignore=255):
+        self.scales, self.ignore_label, self.flip = scales, lb_ignore, flip
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.cropsize = tuple(cropsize) if isinstance(cropsize, (list, tuple)) else (cropsize, cropsize)
+        self.cropstride = cropstride
+
+    def pad_tensor(self, inten):
+        """:667-679 — centre the image in a zero canvas at least as large as the crop."""
+        N_, C_, H, W = inten.shape
+        cropH, cropW = self.cropsize
+        if cropH < H and cropW < W:
+            return inten, [0, H, 0, W]
+        padH, padW = max(cropH, H), max(cropW, W)
+        out = torch.zeros(N_, C_, padH, padW, device=inten.device, dtype=inten.dtype)
+        hst, wst = (padH - H) // 2, (padW - W) // 2
+        out[:, :, hst:hst + H, wst:wst + W] = inten
+        return out, [hst, hst + H, wst, wst + W]
+
+    def chips(self, H, W):
+        """:697-709 — chip origins of the padded scale-level image."""
+        cropH, cropW = self.cropsize
+        strdH, strdW = math.ceil(cropH * self.cropstride), math.ceil(cropW * self.cropstride)
+        n_h, n_w = math.ceil((H - cropH) / strdH) + 1, math.ceil((W - cropW) / strdW) + 1
+        for i in range(n_h):
+            for j in range(n_w):
+                endH, endW = min(H, strdH * i + cropH), min(W, strdW * j + cropW)
+                yield endH - cropH, endH, endW - cropW, endW
+
+    @torch.no_grad()
+    def __call__(self, net, dl, n_classes):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        acc = SegHist(n_classes, dev, self.ignore_label)
+        for imgs, label in dl:
+            imgs = imgs.to(dev)
+            label = label.squeeze(1).to(dev, non_blocking=True)
+            N_, H, W = label.shape
+            probs = torch.empty(N_, n_classes, H, W, dtype=torch.float32, device=dev)
+            for si, sc in enumerate(self.scales):
+                im = F.interpolate(imgs, [int(H * sc), int(W * sc)], mode='bilinear', align_corners=True)
+                im, window = self.pad_tensor(im)
+                PH, PW = im.shape[-2:]
+                pmap = torch.zeros(N_, n_classes, PH, PW, dtype=torch.float32, device=dev)
+                for y0, y1, x0, x1 in self.chips(PH, PW):
+                    chip = im[:, :, y0:y1, x0:x1]
+                    lg = net(chip)[0]
+                    lgf = net(torch.flip(chip, dims=(3,)))[0] if self.flip else None
+                    for b in range(N_):
+                        ops.eval_chip_accum(lg[b], pmap[b], y0, x0, None if lgf is None else lgf[b], exp_after=self.flip)
+                for b in range(N_):
+                    ops.prob_resize_accum(pmap[b], window, probs[b], first=(si == 0))
+            for b in range(N_):
+                ops.argmax_hist(probs[b], label=label[b], hist=acc.hist, ignore=self.ignore_label, want_pred=False)
+        acc.all_reduce()
+        return acc.miou()
+
+
 class MscEvalV0_Contrast:
     """evaluate.py:101-192 — the evaluator ``eval_model_contrast`` (:1127) and tools/eval_snp.py build as
     ``MscEvalV0_Contrast(configer, (0.5,), False)``.  The net returns the logits tensor itself.  With

@@ -124,6 +124,8 @@ SIGNATURES = {
     "mdseg_label_pipeline": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "mdseg_head_tc16_tile": (_I, [_I]),
     "mdseg_head_fwd_tc16": (_I, [_P, _I, _I, _I, _L, _P, _I, _I, _P, _I, _P]),
+    "mdseg_eval_chip_accum": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "mdseg_prob_resize_accum": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "mdseg_softmax_nchw": (_I, [_P, _I, _I, _I, _L, _P, _P]),
     "mdseg_softmax_bwd_nchw": (_I, [_P, _P, _I, _I, _L, _P, _I, _P]),
     "mdseg_up_nll_fwd": (_I, [C.POINTER(SrcTable), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -1014,6 +1014,34 @@ def argmax_hist(probs, label=None, hist=None, lut=None, ignore=255, want_pred=Tr
     return pred
 
 
+def eval_chip_accum(logits, probs, y0, x0, logits_flip=None, exp_after=False):
+    """probs[:, y0:y0+ch, x0:x0+cw] += softmax(logits) (+ softmax(un-flipped logits_flip)), exp() of the sum when
+    `exp_after` (MscEvalCrop.eval_chip + the window add of crop_eval, evaluate.py:684-710).  logits [C, ch, cw]."""
+    _require_cuda(logits, probs)
+    logits = logits.contiguous()
+    if logits.dtype not in _DT or _DT[logits.dtype] > N.F16:
+        logits = logits.float()
+    if logits_flip is not None:
+        logits_flip = logits_flip.to(logits.dtype).contiguous()
+    Cc, ch, cw = logits.shape
+    if probs.dtype != torch.float32 or not probs.is_contiguous() or probs.shape[0] != Cc:
+        raise ValueError("probs must be a contiguous fp32 [C, PH, PW]")
+    N.call("mdseg_eval_chip_accum", _ptr(logits), _ptr(logits_flip), _DT[logits.dtype], Cc, ch, cw, _ptr(probs),
+           probs.shape[1], probs.shape[2], int(y0), int(x0), int(bool(exp_after)), _stream())
+    return probs
+
+
+def prob_resize_accum(src, window, dst, first=False):
+    """dst (+)= bilinear(align_corners=True) resize of src[:, y0:y1, x0:x1] to dst's size (evaluate.py:722-724)."""
+    _require_cuda(src, dst)
+    y0, y1, x0, x1 = [int(v) for v in window]
+    if src.dtype != torch.float32 or dst.dtype != torch.float32 or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("probability maps are contiguous fp32 [C, H, W]")
+    N.call("mdseg_prob_resize_accum", _ptr(src), src.shape[0], src.shape[1], src.shape[2], y0, x0, y1 - y0, x1 - x0,
+           _ptr(dst), dst.shape[1], dst.shape[2], int(bool(first)), _stream())
+    return dst
+
+
 def label_nearest(label, size):
     """Legacy 'nearest' resize of an integer label map [N,H,W] -> [N,h,w] (evaluate.py:156-157)."""
     _require_cuda(label)

@@ -151,3 +151,53 @@ def test_eval_fused_with_a_downsampling_pass_takes_the_direct_kernels(ops):
     want_pred = ops.argmax_hist(probs, label, want)
     pred, hist = ops.eval_fused(passes, (H, W), label=label)
     assert torch.equal(pred, want_pred) and torch.equal(hist, want)
+
+
+def test_msc_eval_crop_against_the_reference_op_sequence(ops):
+    """MscEvalCrop (evaluate.py:650-753): chips, flip + the reference's exp() of the flipped sum, per-scale bilinear
+    resize of the probability map, arg-max, confusion matrix — against the same op sequence in torch on the GPU."""
+    import math
+    import torch.nn.functional as F
+    from mdseg_b200.dropin.evaluate import MscEvalCrop
+    g = torch.Generator(device=DEV).manual_seed(8)
+    C, H, W = 7, 72, 104
+    wgt = torch.randn(C, 3, 3, 3, generator=g, device=DEV)
+
+    def net(x):  # a fixed "network" with full-resolution logits, like the BiSeNet heads (bisenetv2.py:519)
+        return (F.conv2d(x, wgt, padding=1) * 2.0,)
+
+    imgs = torch.randn(2, 3, H, W, generator=g, device=DEV)
+    label = torch.randint(0, C, (2, 1, H, W), generator=g, device=DEV)
+    label[torch.rand(2, 1, H, W, generator=g, device=DEV) < 0.1] = 255
+    for flip in (True, False):
+        ev = MscEvalCrop(cropsize=48, cropstride=2. / 3, flip=flip, scales=(0.5, 1, 1.5))
+        got = ev(net, [(imgs, label)], C)
+        # the reference's sequence, verbatim in torch
+        hist = torch.zeros(C, C, device=DEV)
+        probs = torch.zeros(2, C, H, W, device=DEV)
+        for sc in ev.scales:
+            im = F.interpolate(imgs, [int(H * sc), int(W * sc)], mode='bilinear', align_corners=True)
+            im, (hst, hed, wst, wed) = ev.pad_tensor(im)
+            PH, PW = im.shape[-2:]
+            prob = torch.zeros(2, C, PH, PW, device=DEV)
+            strd = math.ceil(48 * 2. / 3)
+            n_h, n_w = math.ceil((PH - 48) / strd) + 1, math.ceil((PW - 48) / strd) + 1
+            for i in range(n_h):
+                for j in range(n_w):
+                    endH, endW = min(PH, strd * i + 48), min(PW, strd * j + 48)
+                    stH, stW = endH - 48, endW - 48
+                    chip = im[:, :, stH:endH, stW:endW]
+                    p = net(chip)[0].softmax(dim=1)
+                    if flip:
+                        p = p + net(torch.flip(chip, dims=(3,)))[0].flip(dims=(3,)).softmax(dim=1)
+                        p = torch.exp(p)
+                    prob[:, :, stH:endH, stW:endW] += p
+            probs += F.interpolate(prob[:, :, hst:hed, wst:wed], (H, W), mode='bilinear', align_corners=True)
+        preds = probs.argmax(1)
+        lab = label.squeeze(1)
+        keep = lab != 255
+        hist += torch.bincount(lab[keep] * C + preds[keep], minlength=C * C).view(C, C)
+        ious = hist.diag() / (hist.sum(0) + hist.sum(1) - hist.diag())
+        want = float(np.nanmean(ious.cpu().numpy()))
+        assert abs(got - want) <= 2e-3, (flip, got, want)   # a handful of near-tie pixels may flip their arg-max
+    ops.check_errors(DEV)
