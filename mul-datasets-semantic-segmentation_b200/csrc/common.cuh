@@ -154,6 +154,34 @@ template <> struct VecLoad<__nv_bfloat16, 8> {
     stg_stream_v4(p, make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
   }
 };
+// four 16-bit values per 8-byte load: the forward of the full-resolution CE keeps 8 planes x 4 pixels in registers
+// (8 planes x 8 pixels cost 157 registers and one resident CTA per SM)
+template <> struct VecLoad<__nv_bfloat16, 4> {
+  using Raw = int2;
+  static __device__ __forceinline__ Raw raw(const __nv_bfloat16* p) { return ldg_stream_v2(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[4]) {
+    const uint32_t w[2] = {(uint32_t)r.x, (uint32_t)r.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      o[2 * i] = __uint_as_float(w[i] << 16);
+      o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[4]) { unpack(raw(p), o); }
+};
+template <> struct VecLoad<__half, 4> {
+  using Raw = int2;
+  static __device__ __forceinline__ Raw raw(const __half* p) { return ldg_stream_v2(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[4]) {
+    const uint32_t w[2] = {(uint32_t)r.x, (uint32_t)r.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[4]) { unpack(raw(p), o); }
+};
 template <> struct VecLoad<__nv_bfloat16, 1> {
   using Raw = __nv_bfloat16;
   static __device__ __forceinline__ Raw raw(const __nv_bfloat16* p) { return *p; }

@@ -260,6 +260,159 @@ ce_bwd_nhwc_kernel(const T* __restrict__ logits, const L* __restrict__ labels, i
   }
 }
 
+
+// ---- NHWC (channels_last), tiled: a tile of TP pixels x C channels is CONTIGUOUS in memory -----------------------
+// One persistent 256-thread CTA per SM.  A tile arrives with a single cp.async.bulk (no thread copies anything) into
+// one of two shared-memory stages while the previous tile is being computed; 256 / TP threads share a pixel and walk
+// its channels interleaved (for even C in an order rotated by the pixel index, so that the row stride C does not map
+// the pixels of a warp onto the same banks); the backward overwrites the tile in place and it leaves with one bulk
+// store.  The label-class logit is one direct read instead of a compare per channel.
+#ifndef MDSEG_TILE_THREADS
+#define MDSEG_TILE_THREADS 1024
+#endif
+constexpr int kTileThreads = MDSEG_TILE_THREADS;
+constexpr int kTileStageBytes = 100 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tile_bar_init(uint64_t* b) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32a(b)));
+}
+__device__ __forceinline__ void tile_bar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nMDSEG_TL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MDSEG_TL_DONE;\nbra MDSEG_TL_WAIT;\nMDSEG_TL_DONE:\n}\n" ::"r"(smem_u32a(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tile_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32a(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32a(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32a(bar))
+               : "memory");
+}
+
+// pixels per tile for C channels of `esz` bytes, so that the tile fills (at most) one stage: a multiple of the CTA size
+// (one or more pixels per thread) or, for wide rows, a power of two below it (2 .. 32 threads per pixel); 0 = no fit
+int tile_pixels(int C, int esz) {
+  const size_t fit = (size_t)kTileStageBytes / ((size_t)C * esz);
+  if (fit >= (size_t)kTileThreads) return (int)(fit / kTileThreads > 4 ? 4 : fit / kTileThreads) * kTileThreads;
+  int tp = kTileThreads / 2;
+  while (tp >= 32 && (size_t)tp > fit) tp >>= 1;
+  return tp >= 32 ? tp : 0;
+}
+
+template <typename T, typename L, bool BWD>
+__global__ void __launch_bounds__(kTileThreads, 1)
+ce_nhwc_tile_kernel(const T* __restrict__ logits, const L* __restrict__ labels, int64_t n_tiles, int TP, int C, int ignore,
+                    float* __restrict__ loss_px, float* __restrict__ lse_px, mdseg_ohem_state* st, int* err_flag,
+                    const float* __restrict__ grad_out, float grad_scale, T* __restrict__ dlogits) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  const uint32_t tile_bytes = (uint32_t)TP * C * sizeof(T);
+  const uint32_t stage_stride = (tile_bytes + 127u) & ~127u;
+  const int tpc = TP >= kTileThreads ? 1 : kTileThreads / TP;  // threads per pixel: 1, 2, 4 or 8
+  const int ppt = TP >= kTileThreads ? TP / kTileThreads : 1;  // pixels per thread: 1 .. 8
+  const int part = threadIdx.x % tpc;
+  const bool rotate = (C % 2) == 0;
+  const float thresh = st->thresh;
+  SelParams sp;
+  if (BWD) sp = load_sel(st, grad_out, grad_scale);
+  unsigned n_valid = 0, n_hard = 0, n_px = 0;
+  double sum_hard = 0.0;
+  int err = 0;
+
+  if (threadIdx.x == 0) {
+    tile_bar_init(&bars[0]);
+    tile_bar_init(&bars[1]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int64_t)blockIdx.x < n_tiles)
+      tile_load(tile_smem, logits + (int64_t)blockIdx.x * TP * C, tile_bytes, &bars[0]);
+  }
+  __syncthreads();
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    T* buf = reinterpret_cast<T*>(tile_smem + (size_t)s * stage_stride);
+    // queue the next tile into the other stage (its bulk store of two iterations ago has finished reading)
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {
+      if (BWD) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      tile_load(tile_smem + (size_t)(s ^ 1) * stage_stride, logits + (tile + gridDim.x) * TP * C, tile_bytes, &bars[s ^ 1]);
+    }
+    tile_bar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
+    for (int j = 0; j < ppt; ++j) {
+    const int px = threadIdx.x / tpc + j * kTileThreads;
+    const int rot = rotate ? px % C : 0;
+    const int64_t p = tile * TP + px;
+    T* row = buf + (size_t)px * C;
+    const int lab = load_label<L>(labels, p);
+    const bool ign = lab == ignore, ok = (unsigned)lab < (unsigned)C;
+    if (!BWD) {
+      float m = -FLT_MAX;
+      for (int c = part; c < C; c += tpc) {
+        int cc = c + rot; cc = cc >= C ? cc - C : cc;
+        m = fmaxf(m, to_f32<T>(row[cc]));
+      }
+      for (int o = 1; o < tpc; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float m2 = m * kLog2e;
+      float s0 = 0.f, s1 = 0.f;
+      int c = part;
+      for (; c + tpc < C; c += 2 * tpc) {
+        int ca = c + rot; ca = ca >= C ? ca - C : ca;
+        int cb = c + tpc + rot; cb = cb >= C ? cb - C : cb;
+        s0 += ex2_approx(fmaf(to_f32<T>(row[ca]), kLog2e, -m2));
+        s1 += ex2_approx(fmaf(to_f32<T>(row[cb]), kLog2e, -m2));
+      }
+      if (c < C) {
+        int ca = c + rot; ca = ca >= C ? ca - C : ca;
+        s0 += ex2_approx(fmaf(to_f32<T>(row[ca]), kLog2e, -m2));
+      }
+      float sum = s0 + s1;
+      for (int o = 1; o < tpc; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (part == 0) {
+        const float lse = m + logf(sum);
+        if (!ign && !ok) err |= MDSEG_ERR_LABEL_RANGE;
+        const float l = (ok && !ign) ? (lse - to_f32<T>(row[lab])) : 0.f;
+        loss_px[p] = l;
+        lse_px[p] = lse;
+        n_valid += (ok && !ign) ? 1u : 0u;
+        if (l > thresh) { ++n_hard; sum_hard += (double)l; }
+        ++n_px;
+      }
+    } else {
+      const bool sel = is_selected(sp, loss_px[p]) && ok && !ign;
+      const float w = sel ? sp.w : 0.f;
+      const float lse2 = lse_px[p] * kLog2e;
+      for (int c = part; c < C; c += tpc) {
+        int cc = c + rot; cc = cc >= C ? cc - C : cc;
+        const float pr = ex2_approx(fmaf(to_f32<T>(row[cc]), kLog2e, -lse2));
+        row[cc] = from_f32<T>(w * (pr - ((cc == lab) ? 1.f : 0.f)));
+      }
+    }
+    }  // pixels of this thread
+    if (!BWD) {
+      __syncthreads();  // every thread has read the stage before it is refilled two iterations later
+    } else {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dlogits + tile * TP * C),
+                     "r"(smem_u32a(buf)), "r"(tile_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (BWD) {
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    if (err) atomicOr(err_flag, err);
+    block_accumulate_stats(st, n_valid, n_hard, sum_hard, n_px);
+  }
+}
+
 // ---- launchers ----------------------------------------------------------------
 int grid_for(int64_t work_items, int per_sm) {
   int64_t blocks = ceil_div64(work_items > 0 ? work_items : 1, 256);
@@ -274,10 +427,25 @@ int launch_fwd(const void* logits, int layout, const void* labels, int N, int C,
   const int64_t HW = (int64_t)H * W;
   if (layout == MDSEG_NHWC) {
     const int64_t P = HW * N;
-    ce_fwd_nhwc_kernel<T, L><<<grid_for(P * 32, 8), 256, 0, s>>>((const T*)logits, (const L*)labels, P, C, ignore,
-                                                                  loss_px, lse_px, st, err_flag);
+    // whole tiles through the bulk-copy pipeline, the ragged tail (and shapes whose tile does not fit) warp per pixel
+    const int TP = (((uintptr_t)logits & 15) == 0) ? tile_pixels(C, (int)sizeof(T)) : 0;
+    const int64_t n_tiles = TP ? P / TP : 0;
+    if (n_tiles) {
+      const size_t smem = 2 * (((size_t)TP * C * sizeof(T) + 127) & ~(size_t)127);
+      auto k = ce_nhwc_tile_kernel<T, L, false>;
+      MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+      k<<<grid, kTileThreads, smem, s>>>((const T*)logits, (const L*)labels, n_tiles, TP, C, ignore, loss_px, lse_px, st,
+                                         err_flag, nullptr, 1.f, nullptr);
+      MDSEG_LAUNCH_OK();
+    }
+    const int64_t done = n_tiles * TP;
+    if (done < P)
+      ce_fwd_nhwc_kernel<T, L><<<grid_for((P - done) * 32, 8), 256, 0, s>>>(
+          (const T*)logits + done * C, (const L*)labels + done, P - done, C, ignore, loss_px + done, lse_px + done, st,
+          err_flag);
   } else {
-    constexpr int PXV = 16 / sizeof(T);
+    constexpr int PXV = 4;  // four pixels per thread for every dtype (16-byte fp32 / 8-byte 16-bit loads, 8 planes in flight)
     const bool vec = (HW % PXV == 0) && ((((uintptr_t)logits | (uintptr_t)loss_px | (uintptr_t)lse_px) & 15) == 0);
     if (vec)
       ce_fwd_nchw_kernel<T, L, PXV><<<grid_for(HW / PXV * N, 6), 256, 0, s>>>(
@@ -297,9 +465,23 @@ int launch_bwd(const void* logits, int layout, const void* labels, int N, int C,
   const int64_t HW = (int64_t)H * W;
   if (layout == MDSEG_NHWC) {
     const int64_t P = HW * N;
-    ce_bwd_nhwc_kernel<T, L><<<grid_for(P * 32, 8), 256, 0, s>>>((const T*)logits, (const L*)labels, P, C, ignore,
-                                                                  loss_px, lse_px, st, grad_out, grad_scale,
-                                                                  (T*)dlogits);
+    const int TP = ((((uintptr_t)logits | (uintptr_t)dlogits) & 15) == 0) ? tile_pixels(C, (int)sizeof(T)) : 0;
+    const int64_t n_tiles = TP ? P / TP : 0;
+    if (n_tiles) {
+      const size_t smem = 2 * (((size_t)TP * C * sizeof(T) + 127) & ~(size_t)127);
+      auto k = ce_nhwc_tile_kernel<T, L, true>;
+      MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+      k<<<grid, kTileThreads, smem, s>>>((const T*)logits, (const L*)labels, n_tiles, TP, C, ignore,
+                                         const_cast<float*>(loss_px), const_cast<float*>(lse_px), st, nullptr, grad_out,
+                                         grad_scale, (T*)dlogits);
+      MDSEG_LAUNCH_OK();
+    }
+    const int64_t done = n_tiles * TP;
+    if (done < P)
+      ce_bwd_nhwc_kernel<T, L><<<grid_for((P - done) * 32, 8), 256, 0, s>>>(
+          (const T*)logits + done * C, (const L*)labels + done, P - done, C, ignore, loss_px + done, lse_px + done, st,
+          grad_out, grad_scale, (T*)dlogits + done * C);
   } else {
     constexpr int PXV = 16 / sizeof(T);
     const bool vec = (HW % PXV == 0) && ((((uintptr_t)logits | (uintptr_t)dlogits) & 15) == 0);
