@@ -491,6 +491,13 @@ int mdseg_up_nll_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset
  * out: [n_images, N, hw] fp32 or the feature dtype.  The features are read by TMA as MN-major UMMA operands — no
  * thread touches them. */
 int mdseg_head_tc16_tile(int N);
+/* d prototype: dW[n, k] = sum_{b, p} dy16[b, n, p] * feats[b, k, p] — split-K over pixel slabs, both operands read by
+ * TMA as K-major UMMA operands (the pixel is the contiguous index of both), fixed-order reduction of the per-slab
+ * partials in `workspace` (deterministic).  dy16: the gradient w.r.t. the head's output in the feature dtype,
+ * [n_images, N, hw]; dW: fp32 [N, K], fully overwritten. */
+size_t mdseg_head_dw_tc16_workspace_bytes(int n_images, int K, int64_t hw, int N);
+int mdseg_head_dw_tc16(const void* dy16, const void* feats, int dtype, int n_images, int K, int64_t hw, int N, float* dW,
+                       void* workspace, size_t workspace_bytes, void* stream);
 int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, int K, int64_t hw, const void* proto_t, int ldb,
                         int N, void* out, int out_dtype, void* stream);
 

@@ -177,6 +177,121 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_con
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
 }
 
+// ---- d prototype: dW[n, k] = sum over images and pixels of dy[b, n, p] * feats[b, k, p] -------------------------
+// Both operands have the contraction index (the pixel) contiguous: two K-major TMA operands, no transposition.
+// A CTA takes one 128-row tile of prototypes, one NT-column tile of feature channels and one slab of the pixels of
+// one image; its fp32 partial goes to a workspace slot and a second kernel adds the slots in a fixed order
+// (deterministic).  The tile CTAs of one slab are neighbours in the grid, so operand re-reads hit L2.
+struct DwArgs {
+  float* part;        // [n_slabs_total][m_tiles][n_tiles][128][NT]
+  long long hw, slab; // pixels per image, pixels per slab (multiple of 64)
+  int slabs_per_image, m_tiles, n_tiles, NT, fmt;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) head_tc16_dw_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB,
+                                                                   const __grid_constant__ DwArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full[kNStages], empty[kNStages], acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, mt = tile / a.n_tiles, nt = tile % a.n_tiles;
+  const int slab_id = blockIdx.y, b = slab_id / a.slabs_per_image, sl = slab_id % a.slabs_per_image;
+  const long long p_beg = (long long)sl * a.slab;
+  const long long p_end = (p_beg + a.slab < a.hw) ? p_beg + a.slab : a.hw;
+  const int n_kb = (int)((p_end - p_beg + 63) / 64);
+  const int NT = a.NT;
+  constexpr uint32_t a_bytes = 128 * 128;  // [128 prototype rows][64 px x 2 B]
+  const uint32_t stage_bytes = a_bytes + (uint32_t)NT * 128u;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < NT) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapB) : "memory");
+    for (int s = 0; s < kNStages; ++s) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+    bar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa(&tmem_base_s)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kNStages;
+        if (kb >= kNStages) bar_wait(&empty[s], (uint32_t)((kb / kNStages - 1) & 1));
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        bar_expect(&full[s], stage_bytes);
+        // pixels beyond the slab but inside the image would be counted twice: slabs are whole 64-pixel chunks, and
+        // pixels beyond the image are zero-filled by TMA
+        tma3(st, &mapA, &full[s], (int)(p_beg + (long long)kb * 64), mt * 128, b);
+        tma3(st + a_bytes, &mapB, &full[s], (int)(p_beg + (long long)kb * 64), nt * NT, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // fp32 accumulate, both operands K-major, N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)a.fmt << 7) | ((uint32_t)a.fmt << 10) | ((uint32_t)(NT >> 3) << 17) |
+                             ((uint32_t)(kM >> 4) << 24);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kNStages;
+        bar_wait(&full[s], (uint32_t)((kb / kNStages) & 1));
+        tc_after();
+        const uint32_t aA = sa(smem + (size_t)s * stage_bytes), aB = aA + a_bytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma(tmem_d, desc_sw128(aA + ks * 32, 16, 1024), desc_sw128(aB + ks * 32, 16, 1024), idesc,
+               (kb > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(&empty[s]);
+        if (kb == n_kb - 1) tc_commit(&acc_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    bar_wait(&acc_full, 0);
+    tc_after();
+    float* slot = a.part + ((((long long)slab_id * a.m_tiles + mt) * a.n_tiles + nt) * 128 + row) * NT;
+    for (int c0 = 0; c0 < NT; c0 += 16) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      uint4* o = reinterpret_cast<uint4*>(slot + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    }
+  }
+  tc_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+__global__ void __launch_bounds__(256) head_tc16_dw_reduce_kernel(const DwArgs a, int n_slabs_total, int N, int K,
+                                                                  float* __restrict__ dW) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  const int mt = n / 128, r = n - mt * 128, nt = k / a.NT, c = k - nt * a.NT;
+  float sum = 0.f;
+  for (int s = 0; s < n_slabs_total; ++s)
+    sum += a.part[((((long long)s * a.m_tiles + mt) * a.n_tiles + nt) * 128 + r) * a.NT + c];
+  dW[idx] = sum;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -258,6 +373,78 @@ extern "C" int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, i
   else if (dtype == MDSEG_BF16) MDSEG_H16_LAUNCH(__nv_bfloat16);
   else MDSEG_H16_LAUNCH(__half);
 #undef MDSEG_H16_LAUNCH
+  MDSEG_LAUNCH_OK();
+  return 0;
+}
+
+// pixel slabs per image of the split-K d prototype GEMM: about two waves of CTAs, at least 4096 pixels per slab
+static int dw_slabs_per_image(int n_images, int64_t hw, int tiles) {
+  long long want = (2LL * 2 * mdseg::sm_count() + (long long)n_images * tiles - 1) / ((long long)n_images * tiles);
+  const long long cap = (hw + 4095) / 4096;
+  if (want > cap) want = cap;
+  return (int)(want < 1 ? 1 : want);
+}
+
+extern "C" size_t mdseg_head_dw_tc16_workspace_bytes(int n_images, int K, int64_t hw, int N) {
+  if (n_images <= 0 || K <= 0 || hw <= 0 || N <= 0) return 256;
+  const int NT = mdseg_head_tc16_tile(K);
+  const int n_tiles = (K + NT - 1) / NT, m_tiles = (N + 127) / 128;
+  const int spi = dw_slabs_per_image(n_images, hw, m_tiles * n_tiles);
+  return (size_t)n_images * spi * m_tiles * n_tiles * 128 * NT * 4 + 256;
+}
+
+extern "C" int mdseg_head_dw_tc16(const void* dy16, const void* feats, int dtype, int n_images, int K, int64_t hw, int N,
+                                  float* dW, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mdseg;
+  MDSEG_REQUIRE(dtype == MDSEG_BF16 || dtype == MDSEG_F16, "mdseg_head_dw_tc16: operands must be bf16 or fp16");
+  MDSEG_REQUIRE(n_images > 0 && n_images <= 65535 && K > 0 && N > 0 && hw > 0 && hw % 8 == 0, "mdseg_head_dw_tc16: bad shape");
+  MDSEG_REQUIRE(dy16 && feats && dW && workspace, "mdseg_head_dw_tc16: null pointer");
+  MDSEG_REQUIRE((((uintptr_t)dy16 | (uintptr_t)feats) & 15) == 0, "mdseg_head_dw_tc16: operands must be 16-byte aligned");
+  MDSEG_REQUIRE(workspace_bytes >= mdseg_head_dw_tc16_workspace_bytes(n_images, K, hw, N),
+                "mdseg_head_dw_tc16: workspace too small");
+  EncodeTiledFn enc = encode_fn();
+  MDSEG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    MDSEG_CUDA_OK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
+  DwArgs a;
+  a.NT = mdseg_head_tc16_tile(K);
+  a.n_tiles = (K + a.NT - 1) / a.NT;
+  a.m_tiles = (N + 127) / 128;
+  a.slabs_per_image = dw_slabs_per_image(n_images, hw, a.m_tiles * a.n_tiles);
+  a.slab = ((hw + a.slabs_per_image - 1) / a.slabs_per_image + 63) / 64 * 64;
+  a.slabs_per_image = (int)((hw + a.slab - 1) / a.slab);
+  a.hw = hw;
+  a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  a.part = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const CUtensorMapDataType dt = dtype == MDSEG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap mapA, mapB;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)N, (cuuint64_t)n_images};
+    cuuint64_t strides[2] = {(cuuint64_t)hw * 2, (cuuint64_t)N * hw * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    CUresult r = enc(&mapA, dt, 3, const_cast<void*>(dy16), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MDSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the gradient (CUresult %d)", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)K, (cuuint64_t)n_images};
+    cuuint64_t strides[2] = {(cuuint64_t)hw * 2, (cuuint64_t)K * hw * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)a.NT, 1};
+    CUresult r = enc(&mapB, dt, 3, const_cast<void*>(feats), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MDSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the features (CUresult %d)", (int)r);
+  }
+  const int n_slabs_total = n_images * a.slabs_per_image;
+  const size_t smem = (size_t)kNStages * (128 * 128 + (size_t)a.NT * 128) + 1024;
+  cudaStream_t s = (cudaStream_t)stream;
+  MDSEG_CUDA_OK(cudaFuncSetAttribute(head_tc16_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_tc16_dw_kernel<<<dim3((unsigned)(a.m_tiles * a.n_tiles), (unsigned)n_slabs_total), kThreads, smem, s>>>(mapA, mapB, a);
+  MDSEG_LAUNCH_OK();
+  head_tc16_dw_reduce_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256, 0, s>>>(a, n_slabs_total, N, K, dW);
   MDSEG_LAUNCH_OK();
   return 0;
 }

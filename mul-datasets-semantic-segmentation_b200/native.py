@@ -123,6 +123,8 @@ SIGNATURES = {
     "mdseg_label_nearest": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "mdseg_label_pipeline": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "mdseg_head_tc16_tile": (_I, [_I]),
+    "mdseg_head_dw_tc16_workspace_bytes": (C.c_size_t, [_I, _I, _L, _I]),
+    "mdseg_head_dw_tc16": (_I, [_P, _P, _I, _I, _I, _L, _I, _P, _P, C.c_size_t, _P]),
     "mdseg_head_fwd_tc16": (_I, [_P, _I, _I, _I, _L, _P, _I, _I, _P, _I, _P]),
     "mdseg_eval_chip_accum": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "mdseg_prob_resize_accum": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),

@@ -601,12 +601,22 @@ class _PrototypeHead(torch.autograd.Function):
         dy = dy.to(torch.float32).contiguous()
         tab = _dense_table(wgt)
         dx = dw = None
-        if ctx.needs_input_grad[0] and _tc16_ok(x):
-            # d feats = dlogits x prototypes^T: the same TMA-fed kernel with the transposed prototypes.  The incoming
-            # gradient is rounded to the feature dtype first (what the reference's autocast backward does to it)
-            dx = torch.empty_like(x)
-            _head_tc16(dy.to(x.dtype), wgt.t(), dx)
-        elif ctx.needs_input_grad[0]:
+        if _tc16_ok(x):
+            # 16-bit features: both gradients on the TMA-fed kernels.  The incoming gradient is rounded to the feature
+            # dtype first (what the reference's autocast backward does to it).
+            dyh = dy.to(x.dtype)
+            if ctx.needs_input_grad[0]:  # d feats = dlogits x prototypes^T: the forward kernel, transposed prototypes
+                dx = torch.empty_like(x)
+                _head_tc16(dyh, wgt.t(), dx)
+            if ctx.needs_input_grad[1]:  # d prototype: split-K over the pixels, both operands K-major
+                dG = torch.empty(Nn, K, dtype=torch.float32, device=x.device)
+                nb = N.lib.mdseg_head_dw_tc16_workspace_bytes(B, K, h * w, Nn)
+                ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+                N.call("mdseg_head_dw_tc16", _ptr(dyh), _ptr(x), _DT[x.dtype], B, K, h * w, Nn, _ptr(dG), _ptr(ws), nb,
+                       _stream())
+                dw = dG.to(ctx.proto_dtype)
+            return dx, dw
+        if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             nb = N.lib.mdseg_proj_bwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
             ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
