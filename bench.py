@@ -233,7 +233,9 @@ def config_of(args, world):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL = {"mdseg_up_ce_bwd_direct": 3, "mdseg_proj_fwd_tc": 2, "mdseg_proj_bwd_tc": 3, "mdseg_proj_bwd_graph_tc": 2,
+KERNELS_PER_CALL = {"mdseg_proj_fwd_tc16": 1, "mdseg_head_fwd_tc16": 1, "mdseg_head_dw_tc16": 2, "mdseg_up_nll_fwd": 1,
+                    "mdseg_up_nll_bwd": 1, "mdseg_softmax_nchw": 1, "mdseg_softmax_bwd_nchw": 1,
+                    "mdseg_up_ce_bwd_direct": 3, "mdseg_proj_fwd_tc": 2, "mdseg_proj_bwd_tc": 3, "mdseg_proj_bwd_graph_tc": 2,
                     "mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
                     "mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
                     "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,

@@ -491,6 +491,13 @@ int mdseg_up_nll_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset
  * out: [n_images, N, hw] fp32 or the feature dtype.  The features are read by TMA as MN-major UMMA operands — no
  * thread touches them. */
 int mdseg_head_tc16_tile(int N);
+/* The DENSE bipartite projection (GNN stage, loss_cross_datasets.py:997-1006) of 16-bit unified logits on the same
+ * kernel: y[b, n, p] = sum_c G_d[n, c] x[b, c, p], d = dataset_ids[b].  graphs_t: host array of n_datasets device
+ * pointers, graph d converted to the logits' dtype and padded like proto_t above ([n_tiles * NT(C_ds[d]), ldb]); a NULL
+ * entry skips the dataset.  y: fp32 [n_images, y_cmax, hw]; rows of images whose dataset is skipped are untouched. */
+int mdseg_proj_fwd_tc16(const void* x, int dtype, int n_images, int C_uni, int64_t hw, const void* const* graphs_t, int ldb,
+                        const int* C_ds /*host*/, int n_datasets, const int32_t* dataset_ids, float* y, int y_cmax,
+                        void* stream);
 /* d prototype: dW[n, k] = sum_{b, p} dy16[b, n, p] * feats[b, k, p] — split-K over pixel slabs, both operands read by
  * TMA as K-major UMMA operands (the pixel is the contiguous index of both), fixed-order reduction of the per-slab
  * partials in `workspace` (deterministic).  dy16: the gradient w.r.t. the head's output in the feature dtype,

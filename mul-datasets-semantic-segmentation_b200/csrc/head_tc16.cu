@@ -73,15 +73,21 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo, uin
          ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+struct alignas(64) BMaps {
+  CUtensorMap m[MDSEG_MAX_DATASETS];  // the B operand (prototypes, or the dense graph of dataset d)
+};
+
 struct HeadArgs {
-  void* out;          // [n_images, N, hw] fp32 or the feature dtype
+  void* out;          // [n_images, out_cstride, hw] fp32 or the feature dtype
   long long hw;
-  int N, NT, n_kb, fmt, out_is_f32;
+  const int32_t* dataset_ids;  // NULL: every image uses B operand 0
+  int Nd[MDSEG_MAX_DATASETS], NTd[MDSEG_MAX_DATASETS];  // output rows / N tile width per B operand
+  int n_datasets, out_cstride, n_kb, fmt;
 };
 
 template <typename TO>
 __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapB,
+                                                                const __grid_constant__ BMaps mapsB,
                                                                 const __grid_constant__ HeadArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -91,7 +97,11 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nz = blockIdx.x, b = blockIdx.z;
   const long long p0 = (long long)blockIdx.y * kM;
-  const int NT = a.NT;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  if (d < 0 || d >= a.n_datasets) return;          // uniform per CTA (images of no dataset: the caller zero-fills)
+  const int NT = a.NTd[d], Nout = a.Nd[d];
+  if (NT == 0 || nz * NT >= Nout) return;
+  const CUtensorMap& mapB = mapsB.m[d];
   const uint32_t b_bytes = (uint32_t)NT * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
   uint32_t tmem_cols = 32;
@@ -155,9 +165,9 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_con
     bar_wait(&acc_full, 0);
     tc_after();
     const int n0 = nz * NT;
-    TO* ob = (TO*)a.out + ((long long)b * a.N + n0) * a.hw;
+    TO* ob = (TO*)a.out + ((long long)b * a.out_cstride + n0) * a.hw;
     for (int c0 = 0; c0 < NT; c0 += 16) {
-      if (n0 + c0 >= a.N) break;
+      if (n0 + c0 >= Nout) break;
       uint32_t r[16];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_con
       if (p < a.hw) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (n0 + c0 + i < a.N) ob[(long long)(c0 + i) * a.hw + p] = from_f32<TO>(__uint_as_float(r[i]));
+          if (n0 + c0 + i < Nout) ob[(long long)(c0 + i) * a.hw + p] = from_f32<TO>(__uint_as_float(r[i]));
       }
     }
   }
@@ -317,17 +327,20 @@ extern "C" int mdseg_head_tc16_tile(int N) {
   return (((N + n_tiles - 1) / n_tiles) + 15) & ~15;
 }
 
-extern "C" int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, int K, int64_t hw, const void* proto_t,
-                                   int ldb, int N, void* out, int out_dtype, void* stream) {
-  using namespace mdseg;
-  MDSEG_REQUIRE(dtype == MDSEG_BF16 || dtype == MDSEG_F16, "mdseg_head_fwd_tc16: features must be bf16 or fp16");
-  MDSEG_REQUIRE(out_dtype == MDSEG_F32 || out_dtype == dtype, "mdseg_head_fwd_tc16: output is fp32 or the feature dtype");
-  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && K > 0 && N > 0 && hw > 0, "mdseg_head_fwd_tc16: bad shape");
+namespace mdseg {
+namespace {
+// A = x [n_images, K, hw] (16-bit, MN-major by TMA); B operand d = bt[d]: [n_tiles(d) * NT(d), ldb] in the same dtype
+int launch_head16(const void* x, int dtype, int n_images, int K, int64_t hw, const void* const* bt, int ldb, const int* Nd,
+                  int n_b, const int32_t* dataset_ids, void* out, int out_cstride, int out_dtype, cudaStream_t s,
+                  const char* who) {
+  MDSEG_REQUIRE(dtype == MDSEG_BF16 || dtype == MDSEG_F16, "%s: inputs must be bf16 or fp16", who);
+  MDSEG_REQUIRE(out_dtype == MDSEG_F32 || out_dtype == dtype, "%s: output is fp32 or the input dtype", who);
+  MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && K > 0 && hw > 0 && n_b > 0 && n_b <= MDSEG_MAX_DATASETS, "%s: bad shape", who);
   MDSEG_REQUIRE(ldb >= K && ldb % 8 == 0 && hw % 8 == 0,
-                "mdseg_head_fwd_tc16: ldb and h * w must be multiples of 8 (16-byte TMA strides), ldb >= K");
+                "%s: ldb and h * w must be multiples of 8 (16-byte TMA strides), ldb >= K", who);
   if (n_images == 0) return 0;
-  MDSEG_REQUIRE(feats && proto_t && out, "mdseg_head_fwd_tc16: null pointer");
-  MDSEG_REQUIRE((((uintptr_t)feats | (uintptr_t)proto_t) & 15) == 0, "mdseg_head_fwd_tc16: operands must be 16-byte aligned");
+  MDSEG_REQUIRE(x && out && bt && Nd, "%s: null pointer", who);
+  MDSEG_REQUIRE(((uintptr_t)x & 15) == 0, "%s: operands must be 16-byte aligned", who);
   EncodeTiledFn enc = encode_fn();
   MDSEG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
   static thread_local bool ctx_bound = false;
@@ -335,39 +348,48 @@ extern "C" int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, i
     MDSEG_CUDA_OK(cudaFree(nullptr));
     ctx_bound = true;
   }
-  const int NT = mdseg_head_tc16_tile(N);
-  const int n_tiles = (N + NT - 1) / NT;
   const CUtensorMapDataType dt = dtype == MDSEG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA;
   {
     cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)K, (cuuint64_t)n_images};
     cuuint64_t strides[2] = {(cuuint64_t)hw * 2, (cuuint64_t)K * hw * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)kKB, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&mapA, dt, 3, const_cast<void*>(feats), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&mapA, dt, 3, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    MDSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the features (CUresult %d)", (int)r);
+    MDSEG_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed for the A operand (CUresult %d)", who, (int)r);
   }
-  {
+  BMaps mapsB;
+  HeadArgs a;
+  a.out = out; a.hw = hw; a.dataset_ids = dataset_ids; a.n_datasets = n_b; a.out_cstride = out_cstride;
+  a.n_kb = (K + kKB - 1) / kKB;
+  a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  int tiles_max = 0, nt_max = 0;
+  for (int d = 0; d < MDSEG_MAX_DATASETS; ++d) {
+    a.Nd[d] = 0; a.NTd[d] = 0;
+    if (d >= n_b || bt[d] == nullptr || Nd[d] <= 0) continue;
+    MDSEG_REQUIRE(((uintptr_t)bt[d] & 15) == 0, "%s: B operand %d must be 16-byte aligned", who, d);
+    const int NT = mdseg_head_tc16_tile(Nd[d]);
+    const int n_tiles = (Nd[d] + NT - 1) / NT;
+    a.Nd[d] = Nd[d]; a.NTd[d] = NT;
+    tiles_max = n_tiles > tiles_max ? n_tiles : tiles_max;
+    nt_max = NT > nt_max ? NT : nt_max;
     cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)(n_tiles * NT)};
     cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
     cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)NT};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&mapB, dt, 2, const_cast<void*>(proto_t), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&mapsB.m[d], dt, 2, const_cast<void*>(bt[d]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    MDSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the prototypes (CUresult %d)", (int)r);
+    MDSEG_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed for B operand %d (CUresult %d)", who, d, (int)r);
   }
-  HeadArgs a;
-  a.out = out; a.hw = hw; a.N = N; a.NT = NT; a.n_kb = (K + kKB - 1) / kKB;
-  a.fmt = dtype == MDSEG_F16 ? 0 : 1; a.out_is_f32 = out_dtype == MDSEG_F32;
-  const size_t smem = (size_t)kNStages * (kABytes + (size_t)NT * 128) + 1024;
-  const dim3 grid((unsigned)n_tiles, (unsigned)((hw + kM - 1) / kM), (unsigned)n_images);
-  cudaStream_t s = (cudaStream_t)stream;
+  if (tiles_max == 0) return 0;
+  const size_t smem = (size_t)kNStages * (kABytes + (size_t)nt_max * 128) + 1024;
+  const dim3 grid((unsigned)tiles_max, (unsigned)((hw + kM - 1) / kM), (unsigned)n_images);
 #define MDSEG_H16_LAUNCH(TO)                                                                              \
   do {                                                                                                    \
     auto k = head_tc16_kernel<TO>;                                                                        \
     MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    k<<<grid, kThreads, smem, s>>>(mapA, mapB, a);                                                        \
+    k<<<grid, kThreads, smem, s>>>(mapA, mapsB, a);                                                       \
   } while (0)
   if (out_dtype == MDSEG_F32) MDSEG_H16_LAUNCH(float);
   else if (dtype == MDSEG_BF16) MDSEG_H16_LAUNCH(__nv_bfloat16);
@@ -375,6 +397,26 @@ extern "C" int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, i
 #undef MDSEG_H16_LAUNCH
   MDSEG_LAUNCH_OK();
   return 0;
+}
+}  // namespace
+}  // namespace mdseg
+
+extern "C" int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, int K, int64_t hw, const void* proto_t,
+                                   int ldb, int N, void* out, int out_dtype, void* stream) {
+  MDSEG_REQUIRE(N > 0 && proto_t, "mdseg_head_fwd_tc16: bad prototypes");
+  const void* bt[1] = {proto_t};
+  const int Nd[1] = {N};
+  return mdseg::launch_head16(feats, dtype, n_images, K, hw, bt, ldb, Nd, 1, nullptr, out, N, out_dtype, (cudaStream_t)stream,
+                              "mdseg_head_fwd_tc16");
+}
+
+extern "C" int mdseg_proj_fwd_tc16(const void* x, int dtype, int n_images, int C_uni, int64_t hw, const void* const* graphs_t,
+                                   int ldb, const int* C_ds, int n_datasets, const int32_t* dataset_ids, float* y, int y_cmax,
+                                   void* stream) {
+  for (int d = 0; d < n_datasets && d < MDSEG_MAX_DATASETS; ++d)
+    MDSEG_REQUIRE(!C_ds || C_ds[d] <= y_cmax, "mdseg_proj_fwd_tc16: y_cmax %d < C_ds %d", y_cmax, C_ds[d]);
+  return mdseg::launch_head16(x, dtype, n_images, C_uni, hw, graphs_t, ldb, C_ds, n_datasets, dataset_ids, y, y_cmax, MDSEG_F32,
+                              (cudaStream_t)stream, "mdseg_proj_fwd_tc16");
 }
 
 // pixel slabs per image of the split-K d prototype GEMM: about two waves of CTAs, at least 4096 pixels per slab

@@ -123,6 +123,7 @@ SIGNATURES = {
     "mdseg_label_nearest": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "mdseg_label_pipeline": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "mdseg_head_tc16_tile": (_I, [_I]),
+    "mdseg_proj_fwd_tc16": (_I, [_P, _I, _I, _I, _L, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_int), _I, _P, _P, _I, _P]),
     "mdseg_head_dw_tc16_workspace_bytes": (C.c_size_t, [_I, _I, _L, _I]),
     "mdseg_head_dw_tc16": (_I, [_P, _P, _I, _I, _I, _L, _I, _P, _P, C.c_size_t, _P]),
     "mdseg_head_fwd_tc16": (_I, [_P, _I, _I, _I, _L, _P, _I, _I, _P, _I, _P]),

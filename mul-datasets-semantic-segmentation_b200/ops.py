@@ -515,12 +515,27 @@ def project(logits_uni, graphs, dataset_ids=None, cache=None):
     cmax = max(g.shape[0] for g in graphs)
     ids = _ids32(dataset_ids, B, x.device)
     y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=x.device)
-    _proj_fwd(x, tab, ids, B, h, w, y, cmax, None, err_flag(x.device))
+    _proj_fwd(x, tab, ids, B, h, w, y, cmax, None, err_flag(x.device), graphs=list(graphs))
     return y
 
 
-def _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef):
-    """mdseg_proj_fwd, or mdseg_proj_fwd_tc (dense graphs on the tensor cores) when a graph is dense."""
+def _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef, graphs=None):
+    """mdseg_proj_fwd, or mdseg_proj_fwd_tc (dense graphs on the tensor cores) when a graph is dense; 16-bit logits
+    with all-dense graphs take the TMA-fed kernel (mdseg_proj_fwd_tc16)."""
+    n = tab.n_datasets
+    if (graphs is not None and x.dtype in (torch.bfloat16, torch.float16) and (h * w) % 8 == 0 and x.data_ptr() % 16 == 0
+            and all(tab.g[i].dense and 8 <= tab.g[i].C_ds <= 1024 for i in range(n)) and tab.C_uni >= 32):
+        ldb = (tab.C_uni + 7) // 8 * 8
+        ptrs, cds, keep = (C.c_void_p * n)(), (C.c_int * n)(), []
+        for i, g in enumerate(graphs):
+            nt = N.lib.mdseg_head_tc16_tile(g.shape[0])
+            gt = torch.zeros(((g.shape[0] + nt - 1) // nt) * nt, ldb, dtype=x.dtype, device=x.device)
+            gt[:g.shape[0], :tab.C_uni] = g.detach().to(x.dtype)
+            keep.append(gt)
+            ptrs[i], cds[i] = gt.data_ptr(), g.shape[0]
+        N.call("mdseg_proj_fwd_tc16", _ptr(x), _DT[x.dtype], B, tab.C_uni, h * w, ptrs, ldb, cds, n, _ptr(ids), _ptr(y), cmax,
+               _stream())
+        return
     if any(tab.g[i].dense for i in range(tab.n_datasets)):
         nbytes = N.lib.mdseg_proj_fwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
@@ -665,7 +680,7 @@ class _MdsProjOhemCE(torch.autograd.Function):
         y = torch.empty(B, cmax, h, w, dtype=torch.float32, device=dev)
         ymax = torch.empty(B, h, w, dtype=torch.float32, device=dev)  # channel maximum of y: the softmax shift
         all_sparse = all(not tab.g[i].dense for i in range(len(Cs)))
-        _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef)
+        _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef, graphs=graphs)
         n_seg = len(Cs) if per_dataset else 1
         src = _src_table([y.data_ptr()] * len(Cs), [cmax * h * w] * len(Cs), Cs, N.F32, per_dataset, c_alloc=cmax,
                          cmax=ymax, cmax_ready=all_sparse)

@@ -31,7 +31,9 @@ for dt in (torch.float32, torch.bfloat16):
         with torch.no_grad():
             return [torch.einsum("bchw,nc->bnhw", x[ids_t == d], graphs[d].to(dt)) for d in range(len(n_cats))]
     alg_bytes = x.numel() * x.element_size() + sum(n_cats[d] for d in ids) * h * w * 4
-    for name, fn in (("tcgen05", tc), ("ffma", ffma), ("torch.einsum", eager)):
+    def tc16():
+        return ops.project(x, graphs, ids_t)
+    for name, fn in (("tcgen05", tc), ("ffma", ffma), ("torch.einsum", eager)) + ((("tcgen05 TMA (ops.project)", tc16),) if dt != torch.float32 else ()):
         for _ in range(3): fn()
         ts = []
         for _ in range(7):
