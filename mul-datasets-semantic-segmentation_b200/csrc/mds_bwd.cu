@@ -47,6 +47,12 @@ constexpr int kStgW28 = 160;                    // one-warp CTAs: staged label c
 constexpr int kMaxR = 5;
 constexpr int kEnt = 384;                       // (class, output channel) pairs of one class group cached in shared memory
 constexpr uint32_t kNoEnt = 0xffffffffu;
+#ifndef MDSEG_BWD_BCAST_PIPE
+#define MDSEG_BWD_BCAST_PIPE 1
+#endif
+#ifndef MDSEG_BWD_CHUNK_LEAN
+#define MDSEG_BWD_CHUNK_LEAN 1
+#endif
 
 // Shared-memory carve-up of ONE warp.  ROW = false: a CTA is one warp owning 28 columns (lane 0 recomputes the halo cell
 // of the strip on its left).  ROW = true: a CTA is the w / 32 warps of a whole low-res row, every lane owns a cell AND a
@@ -201,6 +207,29 @@ __device__ __forceinline__ void broadcast_chunk(const Unit& un, TO* orow, const 
   const bool col_ok = 4 * t < un.ncols;
   TO* base = orow + 4 * t;
   asm volatile("" : "+l"(base));
+#if MDSEG_BWD_BCAST_PIPE
+  // four quads per round: all entry loads first, then the tile rows, then the stores — the round's shared-memory
+  // latencies overlap instead of serialising load -> test -> load -> store four times
+  int q = q0;
+  for (; q + 4 <= q1; q += 4) {
+    uint32_t e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = ents[4 * (q + i) + o];
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(tile + ((e[i] >> 16) & 7u) * OWN + 4 * t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (col_ok && e[i] != kNoEnt) store4(base + (int64_t)((e[i] & 0xffffu) * (uint32_t)hw), v[i]);
+  }
+  for (; q < q1; ++q) {
+    const uint32_t e = ents[4 * q + o];
+    if (col_ok && e != kNoEnt) {
+      const float4 v = *reinterpret_cast<const float4*>(tile + (e >> 16) * OWN + 4 * t);
+      store4(base + (int64_t)((e & 0xffffu) * (uint32_t)hw), v);
+    }
+  }
+#else
 #pragma unroll 4
   for (int q = q0; q < q1; ++q) {
     const uint32_t e = ents[4 * q + o];
@@ -209,6 +238,7 @@ __device__ __forceinline__ void broadcast_chunk(const Unit& un, TO* orow, const 
       store4(base + (int64_t)((e & 0xffffu) * (uint32_t)hw), v);
     }
   }
+#endif
   __syncwarp();
 }
 
@@ -398,9 +428,14 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     __syncwarp();
     if (lane == 0 && q + kStages < un.n_loads) {  // the slot is free: every lane has read its corners
       const int qn = q + kStages;
+#if MDSEG_BWD_CHUNK_LEAN
+      // a class group is one or two chunks (kCG == 2 kKC): no integer division
+      const int qrow = un.n_ch == 2 ? qn >> 1 : qn, qk = un.n_ch == 2 ? qn & 1 : 0;
+#else
+      const int qrow = qn / un.n_ch, qk = qn % un.n_ch;
+#endif
       mbar_expect_tx(&bars[slot], kStageBytes);
-      load_4d(stages + slot * kStageFloats, map, &bars[slot], un.box_x, un.g0 + qn / un.n_ch,
-              un.c_beg + (qn % un.n_ch) * kKC, un.b);
+      load_4d(stages + slot * kStageFloats, map, &bars[slot], un.box_x, un.g0 + qrow, un.c_beg + qk * kKC, un.b);
     }
     if (un.cached && !first_partial) broadcast_chunk<TO, kOwn>(un, orow, ents, eptr[k], eptr[k + 1], tile, a.gm.h * a.gm.w);
   }

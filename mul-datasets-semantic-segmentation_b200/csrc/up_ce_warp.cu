@@ -36,6 +36,15 @@ constexpr int kStageBytes = kStageFloats * 4;   // 2304
 constexpr int kStgW = 176;                      // staged label columns: <= 15 alignment + 32 cells x 5
 constexpr int kMaxR = 5;
 constexpr int kSpan = 160;
+#ifndef MDSEG_FWD_LEAN_FIN
+#define MDSEG_FWD_LEAN_FIN 1
+#endif
+#ifndef MDSEG_FWD_FASTDIV
+#define MDSEG_FWD_FASTDIV 1
+#endif
+#ifndef MDSEG_FWD_CARRY
+#define MDSEG_FWD_CARRY 1
+#endif
 #ifndef MDSEG_FWD_RECUR
 #define MDSEG_FWD_RECUR 0
 #endif
@@ -78,6 +87,9 @@ __device__ __forceinline__ void pick_label2(float2& T, float2 arg, uint32_t lab2
 
 struct Unit {
   int lane, b, x0, xl, sx, nx, C, g0, g1, n_ch, n_loads, Xa, wst, Xw0, nw;
+  int inv_nch;  // ceil(65536 / n_ch)
+  int slot;     // stage of the TMA ring the next chunk arrives in, and its barrier phase
+  uint32_t phase;
   bool cell_ok;
 };
 
@@ -93,7 +105,7 @@ __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, con
 }
 
 template <int RT, bool NX5>
-__device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, const CUtensorMap* cmap, const Unit& un,
+__device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, const CUtensorMap* cmap, Unit& un,
                                          int g, int Ys, int R, int Ys_next, int R_next, const float (&l1w)[5],
                                          const float (&l1h)[kMaxR], float* stages, uint64_t* bars, uint8_t* labs,
                                          float* cms, float* rb, float thresh, unsigned& n_valid, unsigned& n_hard,
@@ -157,15 +169,24 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     s4[j] = 0.f; t4[j] = 0.f;
   }
 
+#if MDSEG_FWD_CARRY
+  uint32_t c2 = 0u;  // fp16 pair (0.0, 0.0): the class ids simply keep counting across the chunks of the cell-row
+#endif
 #pragma unroll 1
   for (int k = 0; k < un.n_ch; ++k) {
     const int q = (g - un.g0) * un.n_ch + k;
-    const int slot = q % kStages;
     const int c_lo = k * kKC;
     const int cc = (un.C - c_lo) < kKC ? (un.C - c_lo) : kKC;
+#if MDSEG_FWD_CARRY
+    const int slot = un.slot;          // ring position and phase are carried, not derived from q by division
+    mbar_wait(&bars[slot], un.phase);
+    if (++un.slot == kStages) { un.slot = 0; un.phase ^= 1u; }
+#else
+    const int slot = q % kStages;
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
-    const float* Sp = stages + slot * kStageFloats + un.xl;
     uint32_t c2 = class_pair(c_lo);
+#endif
+    const float* Sp = stages + slot * kStageFloats + un.xl;
 #pragma unroll 1
     for (int c = 0; c < cc; ++c, c2 = next_class2(c2)) {
       // corners, in log2 units, minus the corner's channel maximum: every interpolated exponent is <= 0
@@ -247,14 +268,63 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     __syncwarp();
     if (lane == 0 && q + kStages < un.n_loads) {  // the slot is free: every lane has read its corners
       const int qn = q + kStages;
+#if MDSEG_FWD_FASTDIV
+      const int qrow = (qn * un.inv_nch) >> 16;  // qn / n_ch by a 16-bit reciprocal (qn < 128, n_ch <= 32): no division
+      const int qk = qn - qrow * un.n_ch;
+#else
+      const int qrow = qn / un.n_ch, qk = qn % un.n_ch;
+#endif
       mbar_expect_tx(&bars[slot], kStageBytes);
-      load_4d(stages + slot * kStageFloats, map, &bars[slot], un.x0, un.g0 + qn / un.n_ch, (qn % un.n_ch) * kKC, un.b);
+      load_4d(stages + slot * kStageFloats, map, &bars[slot], un.x0, un.g0 + qrow, qk * kKC, un.b);
     }
   }
 
   // finalize: lse = M + log2(sum), loss = lse - z_label; rows leave through the warp's row buffer
   const float dm0 = c01 - c00, dm1 = c11 - c10;
   const int off = un.sx - (un.Xw0 - un.Xa);
+#if MDSEG_FWD_LEAN_FIN
+  // straight-line and predicated: this code runs once per cell-row from a cold instruction cache, so every
+  // instruction costs several cycles — no per-pixel branches, per-column terms hoisted, 32-bit row offsets
+  float hm0[NX5 ? 5 : 4], dhm[NX5 ? 5 : 4];
+#pragma unroll
+  for (int i = 0; i < (NX5 ? 5 : 4); ++i) {
+    hm0[i] = fmaf(l1w[i], dm0, c00);
+    dhm[i] = fmaf(l1w[i], dm1, c10) - hm0[i];
+  }
+  float* lp = a.loss_px + (((int64_t)un.b * a.gm.H + Ys) * a.gm.W + un.Xw0);
+  float* ep = a.lse_px + (((int64_t)un.b * a.gm.H + Ys) * a.gm.W + un.Xw0);
+  n_px += (unsigned)(R * un.nx);
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    if (j < R) {  // warp-uniform
+#pragma unroll
+      for (int i = 0; i < (NX5 ? 5 : 4); ++i) {
+        const bool on = i < un.nx;
+        const float sv = i == 4 ? s4[j] : (i & 1 ? S[j][i >> 1].y : S[j][i >> 1].x);
+        const float tv = i == 4 ? t4[j] : (i & 1 ? T[j][i >> 1].y : T[j][i >> 1].x);
+        const uint32_t hv = i == 4 ? (lh4[j] & 0xffffu) : ((LH[j][i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        const bool valid = hv != 0x5bf8u;
+        const float lg = lg2_approx(sv);
+        const float l = valid ? (lg - tv) * kLn2 : 0.f;
+        const float e = (fmaf(l1h[j], dhm[i], hm0[i]) + lg) * kLn2;
+        if (on) { rb[off + i] = l; rb[kSpan + off + i] = e; }
+        const bool hard = on && l > thresh;
+        n_valid += (on && valid) ? 1u : 0u;
+        n_hard += hard ? 1u : 0u;
+        sum_hard += hard ? l : 0.f;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int k = lane; k < un.nw; k += 32) {
+        lp[k] = rb[k];
+        ep[k] = rb[kSpan + k];
+      }
+      lp += a.gm.W;
+      ep += a.gm.W;
+      __syncwarp();
+    }
+  }
+#else
 #pragma unroll
   for (int j = 0; j < RT; ++j) {
     if (j < R) {
@@ -285,6 +355,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       __syncwarp();
     }
   }
+#endif
 }
 
 constexpr size_t kOffCm = (size_t)kStages * kStageBytes;
@@ -355,6 +426,8 @@ __global__ void __launch_bounds__(32, MDSEG_FWD_OCC) up_ce_fwd_warp_kernel(const
   un.g0 = g0; un.g1 = g1; un.cell_ok = cell_ok;
   un.n_ch = (un.C + kKC - 1) / kKC;
   un.n_loads = (g1 - g0) * un.n_ch;
+  un.inv_nch = (65536 + un.n_ch - 1) / un.n_ch;
+  un.slot = 0; un.phase = 0u;
   un.Xw0 = Xw0; un.nw = Xw1 - Xw0;
   un.Xa = Xw0 & ~15;
   un.sx = cell_ok ? Xbeg - un.Xa : 0;
@@ -465,7 +538,10 @@ int up_ce_fwd_warp(const FwdArgs& fa, int label_dtype, int n_images, cudaStream_
   Args a;
   a.src = fa.src; a.dataset_ids = fa.dataset_ids; a.labels = (const uint8_t*)fa.labels; a.gm = fa.gm;
   a.ignore = fa.ignore; a.loss_px = fa.loss_px; a.lse_px = fa.lse_px; a.states = fa.states; a.err_flag = fa.err_flag;
-  a.seg_rows = fa.gm.h - 1 < 2 ? fa.gm.h - 1 : 2;
+#ifndef MDSEG_FWD_SEG_ROWS
+#define MDSEG_FWD_SEG_ROWS 2
+#endif
+  a.seg_rows = fa.gm.h - 1 < MDSEG_FWD_SEG_ROWS ? fa.gm.h - 1 : MDSEG_FWD_SEG_ROWS;
   a.n_seg = (fa.gm.h - 1 + a.seg_rows - 1) / a.seg_rows;
   a.n_strips = (fa.gm.w - 1 + 31) / 32;
   MDSEG_CUDA_OK(cudaFuncSetAttribute(up_ce_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
