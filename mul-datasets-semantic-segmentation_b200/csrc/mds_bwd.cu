@@ -50,6 +50,16 @@ constexpr uint32_t kNoEnt = 0xffffffffu;
 #ifndef MDSEG_BWD_BCAST_PIPE
 #define MDSEG_BWD_BCAST_PIPE 1
 #endif
+#ifndef MDSEG_BWD_STAGE_LSE
+#define MDSEG_BWD_STAGE_LSE 1
+#endif
+// timing experiments only (results are wrong when set): no seam wait / no fifth pixel column
+#ifndef MDSEG_BWD_XP_NOSEAM
+#define MDSEG_BWD_XP_NOSEAM 0
+#endif
+#ifndef MDSEG_BWD_XP_NO5
+#define MDSEG_BWD_XP_NO5 0
+#endif
 #ifndef MDSEG_BWD_CHUNK_LEAN
 #define MDSEG_BWD_CHUNK_LEAN 1
 #endif
@@ -155,8 +165,20 @@ __global__ void __launch_bounds__(256) mds_bwd_prep_kernel(const Args a, int64_t
        q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = base + q * 4;
     const float4 ls = *reinterpret_cast<const float4*>(a.loss_px + p);
+    const float lsv[4] = {ls.x, ls.y, ls.z, ls.w};
+#if MDSEG_BWD_STAGE_LSE
+    // only the class byte: the main kernel stages the forward's lse rows and forms log2|w| - lse * log2e itself
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int lv = load_label<L>(labels, p + i);
+      const bool sel = (lv != a.ignore) && ((unsigned)lv < (unsigned)C) && (wabs > 0.f) && is_selected(sp, lsv[i]);
+      packed |= (sel ? (uint32_t)lv : 255u) << (8 * i);
+    }
+    (void)log2w; (void)kInf;
+#else
     const float4 le = *reinterpret_cast<const float4*>(a.lse_px + p);
-    const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, lev[4] = {le.x, le.y, le.z, le.w};
+    const float lev[4] = {le.x, le.y, le.z, le.w};
     float o[4];
     uint32_t packed = 0;
 #pragma unroll
@@ -167,6 +189,7 @@ __global__ void __launch_bounds__(256) mds_bwd_prep_kernel(const Args a, int64_t
       packed |= (sel ? (uint32_t)lv : 255u) << (8 * i);
     }
     *reinterpret_cast<float4*>(a.lw2 + p) = make_float4(o[0], o[1], o[2], o[3]);
+#endif
     *reinterpret_cast<uint32_t*>(a.sel8 + p) = packed;
   }
 }
@@ -183,7 +206,7 @@ __device__ __forceinline__ void zero_rows(const Args& a, TO* outb, int u, int r0
 struct Unit {
   int lane, b, seg, x, x0, ncols, xl, sx, nx, c_beg, c_end, n_ch, g0, g1, box_x, n_loads, Xa, wst;
   bool own, cached;
-  float w_signed, wsign;
+  float w_signed, wsign, log2w;
 };
 
 // four consecutive elements of a gradient row
@@ -267,7 +290,7 @@ __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int
   mbar_expect_tx(sbar, (uint32_t)(R * un.wst * 5));
   for (int j = 0; j < R; ++j) {
     const int64_t p = ((int64_t)un.b * a.gm.H + (Ys + j)) * a.gm.W + un.Xa;
-    bulk_g2s(lw2s + j * STGW, a.lw2 + p, (uint32_t)(un.wst * 4), sbar);
+    bulk_g2s(lw2s + j * STGW, (MDSEG_BWD_STAGE_LSE ? a.lse_px : a.lw2) + p, (uint32_t)(un.wst * 4), sbar);
     bulk_g2s(labs + j * STGW, a.sel8 + p, (uint32_t)un.wst, sbar);
   }
 }
@@ -298,8 +321,13 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       t[i] = -kInf;
       hv[i] = 255u;
       if (j < R && i < un.nx) {
-        t[i] = lw2s[j * kStgW + un.sx + i];
         hv[i] = labs[j * kStgW + un.sx + i];
+#if MDSEG_BWD_STAGE_LSE
+        const float off2 = fmaf(-lw2s[j * kStgW + un.sx + i], kLog2e, un.log2w);  // staged: the forward's lse
+        t[i] = hv[i] != 255u ? off2 : -kInf;
+#else
+        t[i] = lw2s[j * kStgW + un.sx + i];
+#endif
       }
       hv[i] = (uint32_t)__half_as_ushort(__ushort2half_rn((unsigned short)hv[i]));
     }
@@ -333,7 +361,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
 
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
     const int xs = q & 1;  // exchange slot of this chunk
-    if (ROW && xmine != nullptr && q >= 2) mbar_wait(&xbar_mine[2 + xs], (uint32_t)(((q >> 1) - 1) & 1));
+    if (ROW && xmine != nullptr && q >= 2 && !MDSEG_BWD_XP_NOSEAM) mbar_wait(&xbar_mine[2 + xs], (uint32_t)(((q >> 1) - 1) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
     // corners of the next class are fetched while the current one is being computed (the loop stays rolled)
     float n00 = Sp[0], n01 = Sp[1], n10 = Sp[kBoxW], n11 = Sp[kBoxW + 1];
@@ -407,7 +435,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     }
     if (ROW) {
       if (xmine != nullptr && lane == 31) mbar_arrive(&xbar_mine[xs]);  // release: the slot is full
-      if (xleft != nullptr) {
+      if (xleft != nullptr && !MDSEG_BWD_XP_NOSEAM) {
         // column x0 also receives the right-column sums of the last cell of the warp on the left: lane c adds those of
         // class c to the finished row (or to the scratch half of a segment's first row) and to the carry
         mbar_wait(&xbar_left[xs], (uint32_t)((q >> 1) & 1));
@@ -510,7 +538,7 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
     l1w[i] = 0.f;
     if (i < nx) axis_cell(gm.xm, Xbeg + i, cell, l1w[i]);
   }
-  const bool nx5 = __any_sync(0xffffffffu, nx > 4);
+  const bool nx5 = MDSEG_BWD_XP_NO5 ? false : __any_sync(0xffffffffu, nx > 4);
 
   Unit un;
   un.lane = lane; un.b = b; un.seg = seg; un.x = x; un.nx = nx; un.c_beg = c_beg; un.c_end = c_end;
@@ -524,6 +552,7 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
   un.sx = cell_ok ? Xbeg - un.Xa : 0;
   un.wst = (gm.W - un.Xa) < kStgW ? (gm.W - un.Xa) : kStgW;
   un.w_signed = wsel; un.wsign = wsel < 0.f ? -1.f : 1.f;
+  un.log2w = log2f(fabsf(wsel));  // -inf when nothing is selected or the incoming gradient is 0: every term vanishes
   un.cached = false;
 
   if (lane == 0) {
