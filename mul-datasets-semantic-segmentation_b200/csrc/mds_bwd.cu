@@ -50,12 +50,12 @@ constexpr uint32_t kNoEnt = 0xffffffffu;
 #ifndef MDSEG_BWD_BCAST_PIPE
 #define MDSEG_BWD_BCAST_PIPE 1
 #endif
-#ifndef MDSEG_BWD_STAGE_LSE
-#define MDSEG_BWD_STAGE_LSE 1
+// timing experiments only (wrong results when set): lite warps do not load their fifth-column sums / no fifth column
+#ifndef MDSEG_BWD_XP_NOLD
+#define MDSEG_BWD_XP_NOLD 0
 #endif
-// timing experiments only (results are wrong when set): no seam wait / no fifth pixel column
-#ifndef MDSEG_BWD_XP_NOSEAM
-#define MDSEG_BWD_XP_NOSEAM 0
+#ifndef MDSEG_BWD_XP_NOUSE
+#define MDSEG_BWD_XP_NOUSE 0
 #endif
 #ifndef MDSEG_BWD_XP_NO5
 #define MDSEG_BWD_XP_NO5 0
@@ -81,9 +81,11 @@ struct Lay {
   static constexpr size_t kOffBars = kOffEptr + 16;
   static constexpr size_t kOffXbar = kOffBars + (kStages + 1) * 8;        // ROW: full[2], empty[2]
   static constexpr size_t kOffXchg = kOffXbar + 4 * 8;                    // ROW: [2 slots][kKC][2] floats
-  static constexpr size_t kSmem = ROW ? ((kOffXchg + 2 * kKC * 2 * 4 + 127) / 128) * 128 : kOffXbar;
+  static constexpr size_t kOffC5 = (kOffXchg + 2 * kKC * 2 * 4 + 15) / 16 * 16;        // ROW: [kStages][kKC] float2 fifth-column sums
+  static constexpr size_t kSmem = ROW ? ((kOffC5 + (size_t)kStages * kKC * 8 + 127) / 128) * 128 : kOffXbar;
   static_assert(kCG / kKC + 1 <= 4, "eptr holds one quad offset per chunk of a class group, plus the end");
-  static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffEnt % 16 == 0 && kOffTile % 16 == 0 && kOffBars % 8 == 0,
+  static_assert(kOffLw % 16 == 0 && kOffLab % 16 == 0 && kOffEnt % 16 == 0 && kOffTile % 16 == 0 && kOffBars % 8 == 0 &&
+                    kOffC5 % 16 == 0,
                 "shared memory carve-up alignment");
 };
 static_assert(Lay<false>::kSmem <= 13568, "16 resident one-warp CTAs per SM need <= 13568 bytes of shared memory each");
@@ -118,8 +120,12 @@ struct Args {
   int zero_invalid;  // images with an out-of-range dataset id get zeros in out_base[0]
   float* scrA;       // [n_images][n_seg][c_scr][w]: upper-row half of the first row of a segment
   float* scrB;       // same shape: lower-row half left over by the segment above
-  float* lw2;        // [n_images*H*W]: log2|w| - lse*log2e for pixels with a gradient, -inf otherwise
   uint8_t* sel8;     // [n_images*H*W]: class of the pixel, 255 = no gradient
+  unsigned lite_mask;                  // row CTAs: strips (warps) whose fifth column comes from col5 (host's pick)
+  unsigned char lite_strip[kMaxRowWarps];  // the same strips as a list, n_lite long
+  int n_lite;
+  int c5s;           // class stride of col5: c_scr rounded up to whole chunks (16-byte aligned bulk copies)
+  float2* col5;      // row CTAs: [n_images][h-1][w/32][c5s] fifth-column sums (cu, t1) of a strip's one 5-column cell
   int c_scr;
   int seg_rows, n_seg, n_strips;
 };
@@ -129,6 +135,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// predicated 8-byte shared-memory store (one instruction; an `if` costs a divergent branch around the address code)
+__device__ __forceinline__ void sts2_if(uint32_t on, uint32_t addr, float a, float b) {
+  asm volatile("{ .reg .pred q;\n  setp.ne.u32 q, %0, 0;\n  @q st.shared.v2.f32 [%1], {%2, %3}; }"
+               :: "r"(on), "r"(addr), "f"(a), "f"(b) : "memory");
 }
 
 // e -= |w| where the pixel's class (fp16 pair `lab2`) equals the current class (`c2`): one packed compare, two
@@ -142,7 +154,10 @@ __device__ __forceinline__ void sub_onehot2(float2& e, uint32_t lab2, uint32_t c
       : "r"(lab2), "r"(c2), "f"(nwabs));
 }
 
-// ---- pass 0: selection state of every label pixel in the form the main kernel consumes --------------------
+// ---- pass 0: selection state of every label pixel in the form the main kernel consumes: the class byte of the
+// pixels with a gradient, 255 for the others (the exponent offset log2|w| - lse * log2e is formed by the main kernel
+// from the forward's lse rows).  16 pixels per thread and round: four 16-byte loss loads, one 16-byte label load for
+// uint8 labels, one 16-byte store.
 template <typename L>
 __global__ void __launch_bounds__(256) mds_bwd_prep_kernel(const Args a, int64_t px_per_image) {
   const int b = blockIdx.y;
@@ -156,41 +171,40 @@ __global__ void __launch_bounds__(256) mds_bwd_prep_kernel(const Args a, int64_t
     sp.thresh = st->thresh; sp.kth = st->kth; sp.mode = st->mode;
     sp.w = (a.grad_out ? a.grad_out[a.src.seg_per_dataset ? d : 0] : 1.f) * a.grad_scale * st->inv_n_sel;
   }
-  const float wabs = fabsf(sp.w);
-  const float log2w = log2f(wabs);
-  const float kInf = __int_as_float(0x7f800000);
+  const bool any = valid_ds && fabsf(sp.w) > 0.f;
   const L* labels = (const L*)a.labels;
+  const bool lab16 = ((uintptr_t)a.labels & 15) == 0;
   const int64_t base = (int64_t)b * px_per_image;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < px_per_image / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < px_per_image / 16;
        q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = base + q * 4;
-    const float4 ls = *reinterpret_cast<const float4*>(a.loss_px + p);
-    const float lsv[4] = {ls.x, ls.y, ls.z, ls.w};
-#if MDSEG_BWD_STAGE_LSE
-    // only the class byte: the main kernel stages the forward's lse rows and forms log2|w| - lse * log2e itself
-    uint32_t packed = 0;
+    const int64_t p = base + q * 16;
+    float4 ls[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int lv = load_label<L>(labels, p + i);
-      const bool sel = (lv != a.ignore) && ((unsigned)lv < (unsigned)C) && (wabs > 0.f) && is_selected(sp, lsv[i]);
-      packed |= (sel ? (uint32_t)lv : 255u) << (8 * i);
-    }
-    (void)log2w; (void)kInf;
-#else
-    const float4 le = *reinterpret_cast<const float4*>(a.lse_px + p);
-    const float lev[4] = {le.x, le.y, le.z, le.w};
-    float o[4];
-    uint32_t packed = 0;
+    for (int v = 0; v < 4; ++v) ls[v] = __ldcs(reinterpret_cast<const float4*>(a.loss_px + p) + v);
+    uint32_t lab[16];
+    if (sizeof(L) == 1 && lab16) {
+      const uint4 lv = *reinterpret_cast<const uint4*>((const uint8_t*)a.labels + p);
+      const uint32_t wv[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int lv = load_label<L>(labels, p + i);
-      const bool sel = (lv != a.ignore) && ((unsigned)lv < (unsigned)C) && (wabs > 0.f) && is_selected(sp, lsv[i]);
-      o[i] = sel ? fmaf(-lev[i], kLog2e, log2w) : -kInf;
-      packed |= (sel ? (uint32_t)lv : 255u) << (8 * i);
+      for (int i = 0; i < 16; ++i) lab[i] = (wv[i >> 2] >> (8 * (i & 3))) & 0xffu;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) lab[i] = (uint32_t)load_label<L>(labels, p + i);
     }
-    *reinterpret_cast<float4*>(a.lw2 + p) = make_float4(o[0], o[1], o[2], o[3]);
-#endif
-    *reinterpret_cast<uint32_t*>(a.sel8 + p) = packed;
+    uint32_t out[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float lsv[4] = {ls[v].x, ls[v].y, ls[v].z, ls[v].w};
+      uint32_t packed = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t lv = lab[4 * v + i];
+        const bool sel = any && (lv != (uint32_t)a.ignore) && (lv < (uint32_t)C) && is_selected(sp, lsv[i]);
+        packed |= (sel ? lv : 255u) << (8 * i);
+      }
+      out[v] = packed;
+    }
+    *reinterpret_cast<uint4*>(a.sel8 + p) = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -207,6 +221,9 @@ struct Unit {
   int lane, b, seg, x, x0, ncols, xl, sx, nx, c_beg, c_end, n_ch, g0, g1, box_x, n_loads, Xa, wst;
   bool own, cached;
   float w_signed, wsign, log2w;
+  const float2* c5base;  // lite warps: fifth-column sums of (image, strip, class group) at cell-row 0, else NULL
+  int64_t c5row;         // ... and their stride per cell-row
+  bool has5;             // this lane owns the five-column cell
 };
 
 // four consecutive elements of a gradient row
@@ -283,14 +300,14 @@ __device__ __forceinline__ void store_class(const Args& a, const GraphDev& gd, c
   }
 }
 
-// lane 0: queue the selection state (lw2 + class byte rows) of cell-row g into shared memory
+// lane 0: queue the selection state (lse + class byte rows) of cell-row g into shared memory
 template <int STGW>
 __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int Ys, int R, float* lw2s, uint8_t* labs,
                                               uint64_t* sbar) {
   mbar_expect_tx(sbar, (uint32_t)(R * un.wst * 5));
   for (int j = 0; j < R; ++j) {
     const int64_t p = ((int64_t)un.b * a.gm.H + (Ys + j)) * a.gm.W + un.Xa;
-    bulk_g2s(lw2s + j * STGW, (MDSEG_BWD_STAGE_LSE ? a.lse_px : a.lw2) + p, (uint32_t)(un.wst * 4), sbar);
+    bulk_g2s(lw2s + j * STGW, a.lse_px + p, (uint32_t)(un.wst * 4), sbar);
     bulk_g2s(labs + j * STGW, a.sel8 + p, (uint32_t)un.wst, sbar);
   }
 }
@@ -298,13 +315,19 @@ __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int
 // One cell-row: all class chunks of the unit.  RT rows / 4 (+1 when NX5) columns are the compiled loop bounds.
 // ROW: `xmine` / `xbar_mine` are this warp's exchange slots and their full[2] / empty[2] barriers (it is the producer for
 // the warp on its right), `xleft` / `xbar_left` those of the warp on its left (NULL for the first warp of the row).
+// NX5: some cell of the warp has a fifth pixel column, computed in the class loop (scalar tail).  Row CTAs with exactly
+// one such lane take NX5 = false with `lite`: the sums of that column come precomputed from mds_bwd_col5_kernel (`c5`:
+// the entries of this cell-row's classes, NULL for the other lanes).  A warp with a scalar tail runs ~16 % longer per
+// class than its neighbours, the seam exchange makes the whole row CTA wait for it, and a second instantiation of this
+// function among the warps of one CTA costs instruction-cache misses on top — so the lite warps run the SAME code.
 template <typename TO, int RT, bool NX5, bool ROW>
 __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, const GraphDev& gd, const Unit& un,
                                          TO* outb, int g, int R, int Ys_next, int R_next, const float (&l1w)[5],
                                          const float (&l1h)[kMaxR],
                                          float* stages, uint64_t* bars, float* carry, float* lw2s,
                                          uint8_t* labs, const uint32_t* ents, const int* eptr, float* tile,
-                                         float* xmine, uint64_t* xbar_mine, const float* xleft, uint64_t* xbar_left) {
+                                         float* xmine, uint64_t* xbar_mine, const float* xleft, uint64_t* xbar_left,
+                                         bool lite, const float2* c5sm) {
   constexpr int kOwn = Lay<ROW>::kOwn, kStgW = Lay<ROW>::kStgW;
   const int lane = un.lane;
   const float kInf = __int_as_float(0x7f800000);
@@ -322,12 +345,8 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       hv[i] = 255u;
       if (j < R && i < un.nx) {
         hv[i] = labs[j * kStgW + un.sx + i];
-#if MDSEG_BWD_STAGE_LSE
         const float off2 = fmaf(-lw2s[j * kStgW + un.sx + i], kLog2e, un.log2w);  // staged: the forward's lse
         t[i] = hv[i] != 255u ? off2 : -kInf;
-#else
-        t[i] = lw2s[j * kStgW + un.sx + i];
-#endif
       }
       hv[i] = (uint32_t)__half_as_ushort(__ushort2half_rn((unsigned short)hv[i]));
     }
@@ -361,16 +380,25 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
 
     mbar_wait(&bars[slot], (uint32_t)((q / kStages) & 1));
     const int xs = q & 1;  // exchange slot of this chunk
-    if (ROW && xmine != nullptr && q >= 2 && !MDSEG_BWD_XP_NOSEAM) mbar_wait(&xbar_mine[2 + xs], (uint32_t)(((q >> 1) - 1) & 1));
+    if (ROW && xmine != nullptr && q >= 2) mbar_wait(&xbar_mine[2 + xs], (uint32_t)(((q >> 1) - 1) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
     // corners of the next class are fetched while the current one is being computed (the loop stays rolled)
     float n00 = Sp[0], n01 = Sp[1], n10 = Sp[kBoxW], n11 = Sp[kBoxW + 1];
     uint32_t c2 = class_pair(c_lo);
+    // running shared-memory addresses of the class epilogue (re-derived from c they cost ~15 instructions per class)
+    float* cp = carry + k * kKC * 32 + lane;
+    float* tp = tile + (ROW ? lane : lane - 1);
+    uint32_t xaddr = 0, xprod = 0;  // ROW: lane 31 parks its right-column sums for the warp on the right
+    if (ROW && xmine != nullptr && lane == 31) { xaddr = smem_u32(xmine + xs * kKC * 2); xprod = 1; }
+    asm volatile("" : "+r"(xaddr), "+r"(xprod));
+    const float2* x5p = c5sm + slot * kKC;  // lite: this chunk's fifth-column sums arrived with the class planes
 #pragma unroll 1
     for (int c = 0; c < cc; ++c, c2 = next_class2(c2)) {
       float v00 = n00, v01 = n01, v10 = n10, v11 = n11;
       Sp += 2 * kBoxW;
       if (c + 1 < cc) { n00 = Sp[0]; n01 = Sp[1]; n10 = Sp[kBoxW]; n11 = Sp[kBoxW + 1]; }
+      float2 x5 = make_float2(0.f, 0.f);
+      if (!NX5 && un.has5 && !MDSEG_BWD_XP_NOLD && !MDSEG_BWD_XP_NOUSE) x5 = x5p[c];
       const float dv0 = v01 - v00, dv1 = v11 - v10;
       const float2 V0 = dup2(v00), DV0 = dup2(dv0), V1 = dup2(v10), DV1 = dup2(dv1);
       float2 CU2, UR2, CL2, LR2;
@@ -393,6 +421,10 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
         LR2 = p == 0 ? mul2(L1W[p], t1) : fma2(L1W[p], t1, LR2);
       }
       float CU = CU2.x + CU2.y, ur = UR2.x + UR2.y, CL = CL2.x + CL2.y, lr = LR2.x + LR2.y;
+      if (!NX5 && lite) {  // warp-uniform; (0, 0) and l1w4 == 0 for the lanes without a fifth column
+        CU += x5.x; ur = fmaf(l1w4, x5.x, ur);
+        CL += x5.y; lr = fmaf(l1w4, x5.y, lr);
+      }
       if (NX5) {
         const float h0 = fmaf(l1w4, dv0, v00);
         const float dd = fmaf(l1w4, dv1, v10) - h0;
@@ -415,27 +447,28 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       float gu = __shfl_up_sync(0xffffffffu, ur, 1);
       float gl = __shfl_up_sync(0xffffffffu, lr, 1);
       if (lane == 0) { gu = 0.f; gl = 0.f; }  // ROW: the left warp's part is added after the class loop
-      if (ROW && xmine != nullptr && lane == 31) {
-        xmine[(xs * kKC + c) * 2] = ur;
-        xmine[(xs * kKC + c) * 2 + 1] = lr;
+      if (ROW) {
+        sts2_if(xprod, xaddr, ur, lr);
+        xaddr += 8;
       }
       // vertical: add the lower-row half carried from the cell-row above; the finished row leaves the warp
       const int cg = k * kKC + c;
       const float up = uo + gu;
-      const float rowv = up + carry[cg * 32 + lane];
-      carry[cg * 32 + lane] = lo + gl;
+      const float rowv = up + *cp;
+      *cp = lo + gl;
+      cp += 32;
       if (first_partial) {
         if (un.own) a.scrA[(((int64_t)un.b * a.n_seg + un.seg) * a.c_scr + (c_lo + c)) * a.gm.w + un.x] = up;
-      } else if (un.cached) {
-        if (ROW) tile[c * kOwn + lane] = rowv;
-        else if (lane >= 1 && lane <= kOwn) tile[c * kOwn + lane - 1] = rowv;
+      } else if (ROW || un.cached) {  // row CTAs always cache their channel list (row_route)
+        if (ROW || (lane >= 1 && lane <= kOwn)) *tp = rowv;
       } else {
         store_class<TO>(a, gd, un, outb, cg, g, rowv);
       }
+      tp += kOwn;
     }
     if (ROW) {
       if (xmine != nullptr && lane == 31) mbar_arrive(&xbar_mine[xs]);  // release: the slot is full
-      if (xleft != nullptr && !MDSEG_BWD_XP_NOSEAM) {
+      if (xleft != nullptr) {
         // column x0 also receives the right-column sums of the last cell of the warp on the left: lane c adds those of
         // class c to the finished row (or to the scratch half of a segment's first row) and to the carry
         mbar_wait(&xbar_left[xs], (uint32_t)((q >> 1) & 1));
@@ -462,8 +495,11 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
 #else
       const int qrow = qn / un.n_ch, qk = qn % un.n_ch;
 #endif
-      mbar_expect_tx(&bars[slot], kStageBytes);
+      mbar_expect_tx(&bars[slot], kStageBytes + (un.c5base ? kKC * 8 : 0));
       load_4d(stages + slot * kStageFloats, map, &bars[slot], un.box_x, un.g0 + qrow, un.c_beg + qk * kKC, un.b);
+      if (un.c5base)
+        bulk_g2s(const_cast<float2*>(c5sm) + slot * kKC, un.c5base + (un.g0 + qrow) * un.c5row + qk * kKC, kKC * 8,
+                 &bars[slot]);
     }
     if (un.cached && !first_partial) broadcast_chunk<TO, kOwn>(un, orow, ents, eptr[k], eptr[k + 1], tile, a.gm.h * a.gm.w);
   }
@@ -486,6 +522,7 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
   float* tile = reinterpret_cast<float*>(smem_raw + L::kOffTile);   // [kKC][kOwn] finished rows of one chunk
   int* eptr = reinterpret_cast<int*>(smem_raw + L::kOffEptr);       // [n_ch + 1] first quad of every chunk
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::kOffBars);  // stage ring + staging barrier
+  float2* c5sm = reinterpret_cast<float2*>(smem_raw + (ROW ? L::kOffC5 : 0));  // ROW: [kStages][kKC]
   // ROW: exchange with the neighbouring warps (this warp produces for the one on its right)
   const bool has_right = ROW && wi + 1 < n_w, has_left = ROW && wi > 0;
   uint64_t* xbar_mine = has_right ? reinterpret_cast<uint64_t*>(smem_raw + L::kOffXbar) : nullptr;
@@ -538,7 +575,10 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
     l1w[i] = 0.f;
     if (i < nx) axis_cell(gm.xm, Xbeg + i, cell, l1w[i]);
   }
-  const bool nx5 = MDSEG_BWD_XP_NO5 ? false : __any_sync(0xffffffffu, nx > 4);
+  // fifth pixel columns: none / one lane of a row-CTA warp (sums precomputed, see cell_row) / anything else (class loop)
+  const int n5 = __popc(__ballot_sync(0xffffffffu, nx > 4));
+  const bool lite = ROW && a.col5 != nullptr && n5 == 1 && ((a.lite_mask >> strip) & 1u);
+  const bool nx5 = n5 > 0 && !lite && !MDSEG_BWD_XP_NO5;
 
   Unit un;
   un.lane = lane; un.b = b; un.seg = seg; un.x = x; un.nx = nx; un.c_beg = c_beg; un.c_end = c_end;
@@ -554,6 +594,12 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
   un.w_signed = wsel; un.wsign = wsel < 0.f ? -1.f : 1.f;
   un.log2w = log2f(fabsf(wsel));  // -inf when nothing is selected or the incoming gradient is 0: every term vanishes
   un.cached = false;
+  un.has5 = lite && nx > 4 && !MDSEG_BWD_XP_NO5;
+  un.c5base = nullptr; un.c5row = 0;
+  if (lite && !MDSEG_BWD_XP_NO5 && !MDSEG_BWD_XP_NOLD) {
+    un.c5row = (int64_t)(w / 32) * a.c5s;
+    un.c5base = a.col5 + ((int64_t)b * (h - 1) * (w / 32) + strip) * a.c5s + c_beg;
+  }
 
   if (lane == 0) {
     prefetch_map(map);
@@ -567,9 +613,11 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
       issue_staging<kStgW>(a, un, Ys0, Ye0 - Ys0, lw2s, labs, &bars[kStages]);
     }
     for (int qn = 0; qn < kStages && qn < un.n_loads; ++qn) {
-      mbar_expect_tx(&bars[qn], kStageBytes);
+      mbar_expect_tx(&bars[qn], kStageBytes + (un.c5base ? kKC * 8 : 0));
       load_4d(stages + qn * kStageFloats, map, &bars[qn], un.box_x, g0 + qn / un.n_ch, c_beg + (qn % un.n_ch) * kKC,
               b);
+      if (un.c5base)
+        bulk_g2s(c5sm + qn * kKC, un.c5base + (g0 + qn / un.n_ch) * un.c5row + (qn % un.n_ch) * kKC, kKC * 8, &bars[qn]);
     }
   }
   for (int cg = 0; cg < kCG; ++cg) carry[cg * 32 + lane] = 0.f;
@@ -633,7 +681,7 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
     mbar_wait(&bars[kStages], (uint32_t)((g - g0) & 1));
 #define MDSEG_ROW(RT, N5)                                                                                           \
   cell_row<TO, RT, N5, ROW>(a, map, gd, un, outb, g, R, Ye, Rn, l1w, l1h, stages, bars, carry, lw2s, labs, ents, eptr, \
-                            tile, xmine, xbar_mine, xleft, xbar_left)
+                            tile, xmine, xbar_mine, xleft, xbar_left, lite, c5sm)
     if (R <= 4) {
       if (nx5) MDSEG_ROW(4, true); else MDSEG_ROW(4, false);
     } else {
@@ -674,6 +722,73 @@ mds_bwd_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a
         zero_rows<TO>(a, outb, uu, g0, g1, last_seg, x, own);
       }
     }
+  }
+}
+
+// Row CTAs: the fifth pixel column of a warp strip's ONE five-column cell, for every class — what cell_row<N5 = 1>
+// computes in its scalar tail, in the same operation order (the gradient is bit-identical either way), written as
+// (cu, t1) = (upper-row sum, lower-row sum) of that column.  CTA = the candidate strips of cell-row g of image b, one
+// warp each; a warp whose strip has no such cell (or several: those stay in the class loop) leaves at once; lanes walk
+// the classes.  At stride 4 a row has W - 4 (w - 1) five-column cells (4 of 511 at 2048 -> 512).  The host lists the
+// candidate strips (a.lite_strip) only to keep the grid small; whether a strip is taken is decided here and in the main
+// kernel by the same device code.
+__global__ void __launch_bounds__(32 * kMaxRowWarps) mds_bwd_col5_kernel(const Args a) {
+  const Geom& gm = a.gm;
+  const int lane = threadIdx.x & 31, strip = a.lite_strip[threadIdx.x >> 5], n_w = a.gm.w / 32;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
+  if (d < 0 || d >= a.src.n_datasets) return;
+  const int h = gm.h, w = gm.w;
+  const int x = strip * 32 + lane;
+  int Xbeg = 0, Xend = 0;
+  if (x <= w - 2) cell_span(gm.xm, x, gm.W, Xbeg, Xend);
+  const unsigned m5 = __ballot_sync(0xffffffffu, Xend - Xbeg > 4);
+  if (__popc(m5) != 1) return;
+  const int owner = __ffs(m5) - 1;
+  const int xo = strip * 32 + owner;
+  const int X5 = __shfl_sync(0xffffffffu, Xbeg, owner) + 4;
+  int cell;
+  float l1w4;
+  axis_cell(gm.xm, X5, cell, l1w4);
+  int Ys, Ye;
+  cell_span(gm.ym, g, gm.H, Ys, Ye);
+  const int R = Ye - Ys;
+  const int C = a.src.C[d];
+  const mdseg_ohem_state* st = a.states + (a.src.seg_per_dataset ? d : 0);
+  const float wsel = (a.grad_out ? a.grad_out[a.src.seg_per_dataset ? d : 0] : 1.f) * a.grad_scale * st->inv_n_sel;
+  const float log2w = log2f(fabsf(wsel)), nwabs = -fabsf(wsel);
+  const float kInf = __int_as_float(0x7f800000);
+  float l1h[kMaxR], off[kMaxR];
+  int cls[kMaxR];
+#pragma unroll
+  for (int j = 0; j < kMaxR; ++j) {
+    l1h[j] = 0.f; off[j] = -kInf; cls[j] = 255;
+    if (j < R) {
+      axis_cell(gm.ym, Ys + j, cell, l1h[j]);
+      const int64_t p = ((int64_t)b * gm.H + (Ys + j)) * gm.W + X5;
+      cls[j] = a.sel8[p];
+      if (cls[j] != 255) off[j] = fmaf(-a.lse_px[p], kLog2e, log2w);
+    }
+  }
+  const float* yb = (const float*)a.src.base[d] + (int64_t)b * a.src.image_stride[d] + (int64_t)g * w + xo;
+  float2* out = a.col5 + ((((int64_t)b * (h - 1) + g) * n_w + strip) * a.c5s);
+  for (int c = lane; c < C; c += 32) {
+    const float* yc = yb + (int64_t)c * h * w;
+    const float v00 = yc[0], v01 = yc[1], v10 = yc[w], v11 = yc[w + 1];
+    const float dv0 = v01 - v00, dv1 = v11 - v10;
+    const float h0 = fmaf(l1w4, dv0, v00);
+    const float dd = fmaf(l1w4, dv1, v10) - h0;
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) {
+      if (j < R) {
+        float e = ex2_approx(fmaf(fmaf(l1h[j], dd, h0), kLog2e, off[j]));
+        if (cls[j] == c) e += nwabs;
+        t0 += e;
+        t1 = fmaf(l1h[j], e, t1);
+      }
+    }
+    out[c] = make_float2(t0 - t1, t1);
   }
 }
 
@@ -720,7 +835,7 @@ int pick_seg_rows(int h) { return h - 1 < MDSEG_SEG_ROWS ? h - 1 : MDSEG_SEG_ROW
 template <typename L>
 int launch_prep(const Args& a, int n_images, cudaStream_t s) {
   const int64_t ppi = (int64_t)a.gm.H * a.gm.W;
-  int64_t bx = ceil_div64(ppi / 4, 256);
+  int64_t bx = ceil_div64(ppi / 16, 256);
   const int64_t want = ceil_div64((int64_t)sm_count() * 16, n_images);
   if (bx > want) bx = want;
   mds_bwd_prep_kernel<L><<<dim3((unsigned)bx, (unsigned)n_images), 256, 0, s>>>(a, ppi);
@@ -747,6 +862,10 @@ int launch(int label_dtype, const Maps& maps, const Args& a, int n_images, int m
   if (rc) return rc;
   if (row_route(a, ents_fit)) {
     const int n_w = a.gm.w / 32;
+    if (a.col5 != nullptr && a.n_lite > 0) {
+      mds_bwd_col5_kernel<<<dim3((unsigned)(a.gm.h - 1), (unsigned)n_images), 32 * a.n_lite, 0, s>>>(a);
+      MDSEG_LAUNCH_OK();
+    }
     const size_t smem = (size_t)n_w * Lay<true>::kSmem;
     auto k = mds_bwd_kernel<TO, true>;
     MDSEG_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -765,6 +884,39 @@ int launch(int label_dtype, const Maps& maps, const Args& a, int n_images, int m
     MDSEG_LAUNCH_OK();
   }
   return 0;
+}
+
+// fifth-column table of the row CTAs (0 when the width does not take that route)
+size_t col5_bytes(int n_images, int h, int w, int c_max) {
+  if (w % 32 != 0 || w / 32 > kMaxRowWarps || h < 2) return 0;
+  return (size_t)n_images * (h - 1) * (w / 32) * ((c_max + kKC - 1) / kKC * kKC) * sizeof(float2) + 16;
+}
+
+// Strips of 32 cells with exactly one five-column cell (host replica of AxisMap::floor_at — one fp32 multiply and a
+// truncation, the same on both sides; the kernels re-derive the answer and only use this list to prune work).
+void pick_lite_strips(Args& a) {
+  a.lite_mask = 0; a.n_lite = 0;
+  if (a.col5 == nullptr) return;
+  const int w = a.gm.w, W = a.gm.W;
+  int n5[kMaxRowWarps] = {0};
+  int cols = 0, cur = 0;
+  for (int X = 0; X <= W; ++X) {
+    int cell = w - 2;
+    if (X < W) {
+      const int i0 = (int)(a.gm.xm.scale * (float)X);
+      cell = i0 > w - 2 ? w - 2 : i0;
+    }
+    if (X == W || cell != cur) {
+      if (cols > 4 && cur / 32 < kMaxRowWarps) ++n5[cur / 32];
+      cur = cell; cols = 0;
+    }
+    ++cols;
+  }
+  for (int st = 0; st < w / 32 && st < kMaxRowWarps; ++st)
+    if (n5[st] == 1) {
+      a.lite_mask |= 1u << st;
+      a.lite_strip[a.n_lite++] = (unsigned char)st;
+    }
 }
 
 int src_max_c(const mdseg_src_table* s) {
@@ -807,7 +959,7 @@ extern "C" size_t mdseg_mds_bwd_workspace_bytes(const mdseg_src_table* src, cons
   if (fused_route(src, graphs, geom_of(h, w, H, W))) {
     const int sr = pick_seg_rows(h);
     const int n_seg = (h - 1 + sr - 1) / sr;
-    return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W * 5 + 1024;
+    return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W + 1024 + col5_bytes(n_images, h, w, c_max);
   }
   // generic route: two gradient planes + the converted dense graphs of mdseg_proj_bwd_tc
   return 2 * (size_t)n_images * c_max * h * w * 4 + 512 + mdseg_proj_bwd_tc_workspace_bytes(graphs, MDSEG_F32);
@@ -858,6 +1010,8 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
                              workspace_bytes - used, stream);
   }
 
+  MDSEG_REQUIRE(((uintptr_t)loss_px & 15) == 0 && ((uintptr_t)lse_px & 15) == 0,
+                "mdseg_mds_bwd: loss_px / lse_px must be 16-byte aligned");
   Args a;
   a.src = *src; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
   a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
@@ -876,8 +1030,12 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
   a.c_scr = c_max;
   a.scrA = ws;
   a.scrB = ws + (size_t)n_images * a.n_seg * c_max * w;
-  a.lw2 = a.scrB + (size_t)n_images * a.n_seg * c_max * w;
-  a.sel8 = reinterpret_cast<uint8_t*>(a.lw2 + (size_t)n_images * H * W);
+  a.sel8 = reinterpret_cast<uint8_t*>(a.scrB + (size_t)n_images * a.n_seg * c_max * w);
+  a.col5 = col5_bytes(n_images, h, w, c_max)
+               ? reinterpret_cast<float2*>(((uintptr_t)(a.sel8 + (size_t)n_images * H * W) + 15) & ~(uintptr_t)15)
+               : nullptr;
+  a.c5s = (c_max + kKC - 1) / kKC * kKC;
+  pick_lite_strips(a);
   tma::Maps maps;
   if (int rc = tma::make_maps(a.src, gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
   bool ents_fit = true;  // a class group's (class, channel) pairs, each chunk padded to quads, within kEnt
@@ -902,7 +1060,7 @@ extern "C" size_t mdseg_up_ce_bwd_direct_workspace_bytes(const mdseg_src_table* 
   if (gm.W % 16 == 0 && tma::fast_geometry(*src, gm)) {
     const int sr = pick_seg_rows(h);
     const int n_seg = (h - 1 + sr - 1) / sr;
-    return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W * 5 + 1024;
+    return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W + 1024 + col5_bytes(n_images, h, w, c_max);
   }
   size_t planes = 0;  // generic route: two fp32 planes per dataset, [n_images, C_d, h, w] each
   for (int i = 0; i < src->n_datasets; ++i) planes += 2 * (size_t)n_images * src->C[i] * h * w * 4;
@@ -965,6 +1123,8 @@ extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t*
     return 0;
   }
 
+  MDSEG_REQUIRE(((uintptr_t)loss_px & 15) == 0 && ((uintptr_t)lse_px & 15) == 0,
+                "mdseg_mds_bwd: loss_px / lse_px must be 16-byte aligned");
   Args a;
   a.src = *src; a.dataset_ids = dataset_ids; a.labels = labels; a.gm = gm; a.ignore = ignore;
   a.loss_px = loss_px; a.lse_px = lse_px; a.states = states; a.grad_out = grad_out; a.grad_scale = grad_scale;
@@ -982,8 +1142,12 @@ extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t*
   a.c_scr = c_max;
   a.scrA = ws;
   a.scrB = ws + (size_t)n_images * a.n_seg * c_max * w;
-  a.lw2 = a.scrB + (size_t)n_images * a.n_seg * c_max * w;
-  a.sel8 = reinterpret_cast<uint8_t*>(a.lw2 + (size_t)n_images * H * W);
+  a.sel8 = reinterpret_cast<uint8_t*>(a.scrB + (size_t)n_images * a.n_seg * c_max * w);
+  a.col5 = col5_bytes(n_images, h, w, c_max)
+               ? reinterpret_cast<float2*>(((uintptr_t)(a.sel8 + (size_t)n_images * H * W) + 15) & ~(uintptr_t)15)
+               : nullptr;
+  a.c5s = (c_max + kKC - 1) / kKC * kKC;
+  pick_lite_strips(a);
   tma::Maps maps;
   if (int rc = tma::make_maps(a.src, gm, n_images, kBoxW, 2, kKC, &maps)) return rc;
   switch (dst->dtype) {  // identity channel lists: 16 entries per class group
