@@ -74,7 +74,8 @@ def parse():
                          "OHEM selection).  confident: labels constant in blocks of 128 x 128 px and +12 on the unified "
                          "channels of the block's class, so fewer than n_min pixels are hard and the top-k fallback "
                          "(radix select over all 33.5 M losses, ohem_ce_loss.py:87-88) runs and is timed.  mixed: as "
-                         "confident, but the logits of every eighth block predict a wrong class: ~12 % of the pixels "
+                         "confident with blocks of 256 x 256 px, but the logits of every eighth block predict a wrong "
+                         "class: ~12 % of the pixels (+ the block borders) "
                          "are hard (threshold branch) and whole regions carry no gradient, what a partly trained net "
                          "looks like (the backward skips warps without a selected pixel)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -135,7 +136,7 @@ def make_batch(workload, device, seed, images=None, logits="randn"):
         pred[b] = torch.randint(0, n_cats[d], (H, W), generator=dgen, device=device)
     if logits in ("confident", "mixed"):
         # spatially coherent labels (blocks of 32 x 32 low-res cells) that the logits predict: raw id r -> class r % C
-        blk = 32
+        blk = 64 if logits == "mixed" else 32  # mixed: 256 x 256 px regions, two warp strips of the kernels wide
         for b, d in enumerate(ids):
             c = n_cats[d]
             cls = torch.randint(0, c, ((h + blk - 1) // blk, (w + blk - 1) // blk), generator=dgen, device=device)

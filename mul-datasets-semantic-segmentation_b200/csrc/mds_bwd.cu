@@ -312,6 +312,27 @@ __device__ __forceinline__ void issue_staging(const Args& a, const Unit& un, int
   }
 }
 
+// A chunk of a cell-row in which no pixel of the warp is selected: every sum is zero, the finished rows are the
+// carried lower-row sums.  Kept out of line so that the hot class loop keeps its registers and code layout.
+template <bool ROW>
+__device__ __noinline__ void skip_chunk(int lane, int k, int cc, bool own, float* scr_first, int64_t scr_stride,
+                                        float* carry, float* tile, float* xslot) {
+  constexpr int kOwn = Lay<ROW>::kOwn;
+  for (int c = 0; c < cc; ++c) {
+    if (ROW && xslot != nullptr && lane == 31) { xslot[2 * c] = 0.f; xslot[2 * c + 1] = 0.f; }
+    float* cq = carry + (k * kKC + c) * 32 + lane;
+    const float rowv = *cq;
+    *cq = 0.f;
+    if (scr_first != nullptr) {  // first row of a segment: its upper-row half goes to the scratch plane
+      if (own) scr_first[c * scr_stride] = 0.f;
+    } else if (ROW) {
+      tile[c * kOwn + lane] = rowv;
+    } else if (lane >= 1 && lane <= kOwn) {
+      tile[c * kOwn + lane - 1] = rowv;
+    }
+  }
+}
+
 // One cell-row: all class chunks of the unit.  RT rows / 4 (+1 when NX5) columns are the compiled loop bounds.
 // ROW: `xmine` / `xbar_mine` are this warp's exchange slots and their full[2] / empty[2] barriers (it is the producer for
 // the warp on its right), `xleft` / `xbar_left` those of the warp on its left (NULL for the first warp of the row).
@@ -335,6 +356,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
   float2 LW[RT][2];
   float lw4[RT];
   uint32_t LH[RT][2], lh4[RT];  // class ids as fp16 pairs (255.0 = no gradient), compared two at a time
+  uint32_t anysel = 0;          // some pixel of this lane's cell carries a gradient
 #pragma unroll
   for (int j = 0; j < RT; ++j) {
     float t[5];
@@ -356,9 +378,13 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     LH[j][0] = hv[0] | (hv[1] << 16);
     LH[j][1] = hv[2] | (hv[3] << 16);
     lh4[j] = hv[4] | (0x5bf8u << 16);  // high half 255.0: never a class
+    anysel |= (LH[j][0] ^ 0x5bf85bf8u) | (LH[j][1] ^ 0x5bf85bf8u) | (lh4[j] ^ 0x5bf85bf8u);
   }
   __syncwarp();
   if (lane == 0 && g + 1 < un.g1) issue_staging<kStgW>(a, un, Ys_next, R_next, lw2s, labs, &bars[kStages]);
+  // No pixel of the warp's 32 cells is selected (OHEM keeps the hard pixels, and those cluster): every term of this
+  // cell-row is exactly zero, and the class loops shrink to moving the carried lower-row sums into the finished rows.
+  const bool skip = (ROW || un.cached) && !__any_sync(0xffffffffu, anysel != 0);
 
   float2 L1H[RT];
 #pragma unroll
@@ -382,6 +408,12 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
     const int xs = q & 1;  // exchange slot of this chunk
     if (ROW && xmine != nullptr && q >= 2) mbar_wait(&xbar_mine[2 + xs], (uint32_t)(((q >> 1) - 1) & 1));
     const float* Sp = stages + slot * kStageFloats + un.xl;
+    if (skip) {  // warp-uniform
+      skip_chunk<ROW>(lane, k, cc, un.own,
+                      first_partial ? a.scrA + (((int64_t)un.b * a.n_seg + un.seg) * a.c_scr + c_lo) * a.gm.w + un.x
+                                    : nullptr,
+                      a.gm.w, carry, tile, xmine ? xmine + xs * kKC * 2 : nullptr);
+    } else {
     // corners of the next class are fetched while the current one is being computed (the loop stays rolled)
     float n00 = Sp[0], n01 = Sp[1], n10 = Sp[kBoxW], n11 = Sp[kBoxW + 1];
     uint32_t c2 = class_pair(c_lo);
@@ -466,6 +498,7 @@ __device__ __forceinline__ void cell_row(const Args& a, const CUtensorMap* map, 
       }
       tp += kOwn;
     }
+    }  // !skip
     if (ROW) {
       if (xmine != nullptr && lane == 31) mbar_arrive(&xbar_mine[xs]);  // release: the slot is full
       if (xleft != nullptr) {
