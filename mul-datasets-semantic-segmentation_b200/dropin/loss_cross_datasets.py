@@ -16,8 +16,13 @@ What runs where:
         ``d bi_graph``); aux heads from the dataset prototypes (:941-951, :1044-1048) through the fused
         up-sample + OhemCE(0.7) kernels;
   * the prototype contractions ``einsum('bchw,nc->bnhw', feats, unify_prototype[...])`` (:950, :961, :971) — the
-    producer of the unified logits, SURVEY §8 f2 — run on the tcgen05 tensor cores (``ops.prototype_head``: forward,
-    d feats and the split-K d prototype); only the GridSplit variant (:779-809) keeps the library einsum;
+    producer of the unified logits, SURVEY §8 f2 — run on the tcgen05 tensor cores.  With ``FOLD_PROTOTYPES`` (the
+    default) the unified head and the bipartite projection behind it are ONE contraction with
+    ``bi_graphs[i] @ unify_prototype`` (``ops.mds_head_proj_ohem_ce``): the product is associative, so the
+    ``[B, C_uni, h, w]`` unified logits and their gradient never exist; with the switch off the head is its own GEMM
+    (``ops.prototype_head``: forward, d feats and the split-K d prototype) in front of the projection, operation by
+    operation as the reference.  The aux heads (:950) always use ``ops.prototype_head``; only the GridSplit variant
+    (:779-809) keeps the library einsum (its backward masks the unified-logit gradient per class);
   * the graph regularisers (orth / spa / max-enc / adj MSE, init-stage graph and prototype MSE, adversarial BCE /
     MSE terms) act on ``[C_ds, C_uni]``-sized tensors; they are restated with the same torch ops.
 
@@ -34,6 +39,11 @@ from .. import ops
 from . import _reference
 from .class_remap import ClassRemap, ClassRemapOneHotLabel  # noqa: F401  (configs name them: eval(class_remaper))
 from .ohem_ce_loss import MdsOhemCELoss, MdsOhemNLLPlusLoss, OhemCELoss  # noqa: F401
+
+
+# einsum(einsum(feats, prototypes), bi_graph) evaluated as einsum(feats, bi_graph @ prototypes): see ops.fold_prototypes.
+# Module-level so that a run can be switched back to the reference's operation order (tests exercise both).
+FOLD_PROTOTYPES = True
 
 
 def _cfg(configer, *key, default=None):
@@ -122,15 +132,20 @@ class CrossDatasetsCELoss_CLIP(nn.Module):
     def forward(self, preds, target, dataset_ids, is_warmup=False):
         logits = preds['seg']
         text_feature_vecs = preds['prototypes']
+        present = _present_rows(dataset_ids, self.n_datasets)
         if self.with_unify_label:
-            logits = ops.prototype_head(logits, text_feature_vecs[self.n_datasets])  # :692 on tcgen05
             if self._matrices is None or self._matrices[0].device != logits.device:
                 self._matrices = [self.classRemapper.getRemapMatrix(i).to(logits.device)
                                   for i in range(self.n_datasets)]
             graphs = self._matrices
+            if FOLD_PROTOTYPES:  # :692 + :701 as one contraction with remap_matrix @ text features
+                per_ds = ops.mds_head_proj_ohem_ce(logits, text_feature_vecs[self.n_datasets], target, dataset_ids,
+                                                   graphs, float(self.CELoss.thresh), self.CELoss.ignore_lb,
+                                                   per_dataset=True)
+                return _sum_present(per_ds, present)
+            logits = ops.prototype_head(logits, text_feature_vecs[self.n_datasets])  # :692 on tcgen05
         else:
             graphs = [text_feature_vecs[i] for i in range(self.n_datasets)]
-        present = _present_rows(dataset_ids, self.n_datasets)
         per_ds = ops.mds_proj_ohem_ce(logits, target, dataset_ids, graphs, float(self.CELoss.thresh),
                                       self.CELoss.ignore_lb, cache=self._graph_cache, per_dataset=True)
         return _sum_present(per_ds, present)
@@ -164,10 +179,14 @@ class CrossDatasetsCELoss_GNN(nn.Module):
         logits = preds['seg']
         unify_prototype = preds['unify_prototype']
         bi_graphs = preds['bi_graphs']
-        logits = ops.prototype_head(logits, unify_prototype)  # :747 on tcgen05
         present = _present_rows(dataset_ids, self.n_datasets)
-        per_ds = ops.mds_proj_ce_mean(logits, target, dataset_ids, list(bi_graphs)[:self.n_datasets], ignore=255,
-                                      cache=self._graph_cache)
+        if FOLD_PROTOTYPES:  # :747 + :759 as one contraction with bi_graph @ unify_prototype
+            per_ds = ops.mds_head_proj_ce_mean(logits, unify_prototype, target, dataset_ids,
+                                               list(bi_graphs)[:self.n_datasets], ignore=255)
+        else:
+            logits = ops.prototype_head(logits, unify_prototype)  # :747 on tcgen05
+            per_ds = ops.mds_proj_ce_mean(logits, target, dataset_ids, list(bi_graphs)[:self.n_datasets], ignore=255,
+                                          cache=self._graph_cache)
         loss = _sum_present(per_ds, present)
         for i in range(self.n_datasets):
             if not present[i]:
@@ -254,7 +273,10 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
     def _present(self, dataset_ids):
         return _present_rows(dataset_ids, self.n_datasets)
 
-    def _fused_ce(self, logits, target, dataset_ids, graphs, which):
+    def _fused_ce(self, logits, target, dataset_ids, graphs, which, head=None):
+        if head is not None:  # `logits` are the features: einsum :971 and einsum :996-1006 folded into one contraction
+            return ops.mds_head_proj_ohem_ce(logits, head, target, dataset_ids, list(graphs),
+                                             float(self.mdsOhemCELoss.thresh), self.mdsOhemCELoss.ignore_lb)
         return ops.mds_proj_ohem_ce(logits, target, dataset_ids, list(graphs), float(self.mdsOhemCELoss.thresh),
                                     self.mdsOhemCELoss.ignore_lb, cache=self._graph_cache[which])
 
@@ -275,6 +297,7 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
 
         # ---- prototype head (:941-972): tcgen05 GEMMs (ops.prototype_head) ----
         proto_aux = None
+        fold_head = None  # set: `logits` stay the features and the loss folds the prototypes into the graphs
         if unify_prototype is not None and not init_gnn_stage:
             feats = logits
             head = unify_prototype
@@ -291,6 +314,8 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
             if self.GridSpilt:
                 self.M = self.M.to(dev)
                 logits = _GridSplitProjection.apply(feats, head, torch.as_tensor(dataset_ids).to(dev), self.M)
+            elif FOLD_PROTOTYPES:
+                fold_head = head
             else:
                 logits = ops.prototype_head(feats, head)
 
@@ -339,14 +364,14 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
                 cur_iter = self.configer.get('iter')
                 cur_iter = cur_iter % (self.gnn_iters + self.seg_iters) % self.gnn_iters
                 max_rate = float(cur_iter) / self.gnn_iters
-                ce = (max_rate * self._fused_ce(logits, target, dataset_ids, bi_graphs[0::2], 0)
-                      + (1 - max_rate) * self._fused_ce(logits, target, dataset_ids, bi_graphs[1::2], 1))
+                ce = (max_rate * self._fused_ce(logits, target, dataset_ids, bi_graphs[0::2], 0, fold_head)
+                      + (1 - max_rate) * self._fused_ce(logits, target, dataset_ids, bi_graphs[1::2], 1, fold_head))
                 loss = add(loss, ce)
             else:
                 if pairs:
                     raise RuntimeError("2*n_datasets graphs outside the soft/max GNN stage: the reference indexes "
                                        "bi_graphs[i] (:1006) and mixes hard and soft graphs of different datasets")
-                ce = self._fused_ce(logits, target, dataset_ids, bi_graphs, 0)
+                ce = self._fused_ce(logits, target, dataset_ids, bi_graphs, 0, fold_head)
                 loss = ce if loss is None else torch.where(torch.isnan(loss), ce, loss + ce)  # :1076-1079
 
         if init_gnn_stage and adj_matrix is not None:  # :1090-1106

@@ -381,8 +381,9 @@ class BipartiteGraphs:
     (``g.data[...] = ``) need an explicit ``invalidate()``.
     """
 
-    def __init__(self, dense_frac=0.25):
+    def __init__(self, dense_frac=0.25, assume_dense=False):
         self.dense_frac = dense_frac
+        self.assume_dense = assume_dense  # every graph is a real matrix (folded prototypes): never copied to the host
         self._cache = {}
 
     def invalidate(self):
@@ -397,7 +398,7 @@ class BipartiteGraphs:
             raise ValueError("bi_graph must be [C_ds, C_uni]")
         dev = g.device
         ent = {"key": key, "tensor": g, "C_ds": g.shape[0], "C_uni": g.shape[1]}
-        if g.requires_grad:
+        if g.requires_grad or self.assume_dense:
             # trainable graph (GNN stage): dense by definition, decided without copying it to the host —
             # it changes every iteration and a D2H copy per graph per step would serialise the stream
             ent["dense"], ent["nnz"] = True, g.shape[0] * g.shape[1]
@@ -772,6 +773,41 @@ def mds_proj_ohem_ce(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255
     dataset without images: OhemCELoss per dataset, lib/loss/loss_cross_datasets.py:701-708)."""
     return _MdsProjOhemCE.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
                                 bool(per_dataset), *graphs)[0]
+
+
+def fold_prototypes(graphs, proto):
+    """W_d = bi_graphs[d] @ unify_prototype, fp32 [C_ds, K] per dataset (tiny torch matmuls; autograd carries
+    d bi_graph = dW_d proto^T and d proto = sum_d G_d^T dW_d).
+
+    The reference forms the unified logits first and projects them afterwards (lib/loss/loss_cross_datasets.py:971
+    then :996-1006; :747 then :759; :692 then :701): y_d = G_d (P f).  The product is associative, so y_d = (G_d P) f:
+    the [B, C_uni, h, w] unified logits (3 GB at cfg3) and their gradient are never formed, and the per-pixel
+    contraction shrinks from K x C_uni + C_uni x C_ds to K x C_ds multiply-adds (512 x 358 + 358 x 61 -> 512 x 61)."""
+    p32 = proto.to(torch.float32)
+    return [g.to(torch.float32) @ p32 for g in graphs]
+
+
+_folded_graphs = None
+
+
+def _folded_cache():
+    global _folded_graphs
+    if _folded_graphs is None:
+        _folded_graphs = BipartiteGraphs(assume_dense=True)
+    return _folded_graphs
+
+
+def mds_head_proj_ohem_ce(feats, proto, labels, dataset_ids, graphs, thresh, ignore=255, cache=None, per_dataset=False):
+    """MdsOhemCELoss(upsample(einsum(einsum(feats, proto), graph[dataset]))) with the two contractions folded into one
+    (see fold_prototypes): the fused loss runs on the features [B, K, h, w] with W_d in the role of the dense graph —
+    forward, d feats and d W_d on the tcgen05 kernels, no unified-logits tensor."""
+    return mds_proj_ohem_ce(feats, labels, dataset_ids, fold_prototypes(graphs, proto), thresh, ignore,
+                            cache or _folded_cache(), per_dataset)
+
+
+def mds_head_proj_ce_mean(feats, proto, labels, dataset_ids, graphs, ignore=255, cache=None):
+    """mds_proj_ce_mean on the features with folded prototypes (see fold_prototypes)."""
+    return mds_proj_ce_mean(feats, labels, dataset_ids, fold_prototypes(graphs, proto), ignore, cache or _folded_cache())
 
 
 def mds_proj_ce_mean(logits_uni, labels, dataset_ids, graphs, ignore=255, cache=None):
