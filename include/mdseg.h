@@ -507,6 +507,22 @@ int mdseg_head_dw_tc16(const void* dy16, const void* feats, int dtype, int n_ima
                        void* workspace, size_t workspace_bytes, void* stream);
 int mdseg_head_fwd_tc16(const void* feats, int dtype, int n_images, int K, int64_t hw, const void* proto_t, int ldb,
                         int N, void* out, int out_dtype, void* stream);
+/* The two adjoints of mdseg_proj_fwd_tc16 (autograd replay of the einsum at loss_cross_datasets.py:997-1006 under
+ * amp.autocast; with folded prototypes — bi_graph @ unify_prototype in the role of the graph and the features in the
+ * role of x — also of the head einsum :971) on the same TMA-fed tcgen05 kernels.
+ * dy16: [n_images, y_cmax, hw] in the dtype of x, planes >= C_ds[dataset] of an image ZERO.
+ * mdseg_proj_bwd_tc16: dx[b, c, p] = sum_n G_d[n, c] dy16[b, n, p].  graphs_tt[d]: G_d transposed, in that dtype,
+ * [n_tiles * NT(C_uni), ldb] (ldb >= y_cmax, ldb % 8 == 0, rows >= C_uni and columns >= C_ds zero).  dx: [n_images, C_uni,
+ * hw] fp32 or that dtype, fully written (zeros for images whose dataset id is out of range).
+ * mdseg_proj_bwd_graph_tc16: dG[d][n, c] = sum over the images b of dataset d and pixels p of dy16[b, n, p] x[b, c, p]:
+ * split-K over pixel slabs, fixed-order reduction per dataset (deterministic).  dG: fp32 [n_datasets, y_cmax, C_uni],
+ * fully overwritten (zeros for a dataset without images). */
+int mdseg_proj_bwd_tc16(const void* dy16, int dtype, int n_images, int y_cmax, int64_t hw, const void* const* graphs_tt,
+                        int ldb, int C_uni, int n_datasets, const int32_t* dataset_ids, void* dx, int dx_dtype, void* stream);
+size_t mdseg_proj_bwd_graph_tc16_workspace_bytes(int n_images, int C_uni, int64_t hw, int y_cmax);
+int mdseg_proj_bwd_graph_tc16(const void* dy16, const void* x, int dtype, int n_images, int C_uni, int64_t hw, int y_cmax,
+                              const int32_t* dataset_ids, int n_datasets, float* dG, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 /* ---- MscEvalCrop (evaluate.py:650-753): sliding-window evaluation ------------------------------------------
  * probs[c, y0 + y, x0 + x] += g(softmax_c(logits)[c, y, x] (+ softmax_c(logits_flip)[c, y, cw - 1 - x])) for one chip

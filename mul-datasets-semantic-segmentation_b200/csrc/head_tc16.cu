@@ -83,6 +83,7 @@ struct HeadArgs {
   const int32_t* dataset_ids;  // NULL: every image uses B operand 0
   int Nd[MDSEG_MAX_DATASETS], NTd[MDSEG_MAX_DATASETS];  // output rows / N tile width per B operand
   int n_datasets, out_cstride, n_kb, fmt;
+  int zero_N, zero_NT;  // zero_N > 0: images of no dataset get zeros in their zero_N output rows (tiles of zero_NT)
 };
 
 template <typename TO>
@@ -98,7 +99,18 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_con
   const int nz = blockIdx.x, b = blockIdx.z;
   const long long p0 = (long long)blockIdx.y * kM;
   const int d = a.dataset_ids ? a.dataset_ids[b] : 0;
-  if (d < 0 || d >= a.n_datasets) return;          // uniform per CTA (images of no dataset: the caller zero-fills)
+  if (d < 0 || d >= a.n_datasets) {                 // uniform per CTA: an image of no dataset
+    if (a.zero_N > 0) {                             // gradient route: its rows are zero (else the caller zero-fills)
+      const int n0 = nz * a.zero_NT;
+      TO* ob = (TO*)a.out + ((long long)b * a.out_cstride + n0) * a.hw;
+      for (int i = threadIdx.x; i < a.zero_NT * kM; i += kThreads) {
+        const int c = i / kM;
+        const long long p = p0 + (i - c * kM);
+        if (n0 + c < a.zero_N && p < a.hw) ob[(long long)c * a.hw + p] = from_f32<TO>(0.f);
+      }
+    }
+    return;
+  }
   const int NT = a.NTd[d], Nout = a.Nd[d];
   if (NT == 0 || nz * NT >= Nout) return;
   const CUtensorMap& mapB = mapsB.m[d];
@@ -290,16 +302,22 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_dw_kernel(const __grid_
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
 }
 
+// dataset_ids == NULL: one sum over every slab -> dW [N, K].  Otherwise blockIdx.y is a dataset and only the slabs of
+// its images are added -> dW [n_datasets, N, K] (d bi_graph of the dense projection, one matrix per dataset).
 __global__ void __launch_bounds__(256) head_tc16_dw_reduce_kernel(const DwArgs a, int n_slabs_total, int N, int K,
+                                                                  const int32_t* __restrict__ dataset_ids,
                                                                   float* __restrict__ dW) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * K) return;
   const int n = idx / K, k = idx - n * K;
   const int mt = n / 128, r = n - mt * 128, nt = k / a.NT, c = k - nt * a.NT;
+  const int d = (int)blockIdx.y;
   float sum = 0.f;
-  for (int s = 0; s < n_slabs_total; ++s)
+  for (int s = 0; s < n_slabs_total; ++s) {
+    if (dataset_ids != nullptr && dataset_ids[s / a.slabs_per_image] != d) continue;
     sum += a.part[((((long long)s * a.m_tiles + mt) * a.n_tiles + nt) * 128 + r) * a.NT + c];
-  dW[idx] = sum;
+  }
+  dW[(long long)d * N * K + idx] = sum;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -332,7 +350,7 @@ namespace {
 // A = x [n_images, K, hw] (16-bit, MN-major by TMA); B operand d = bt[d]: [n_tiles(d) * NT(d), ldb] in the same dtype
 int launch_head16(const void* x, int dtype, int n_images, int K, int64_t hw, const void* const* bt, int ldb, const int* Nd,
                   int n_b, const int32_t* dataset_ids, void* out, int out_cstride, int out_dtype, cudaStream_t s,
-                  const char* who) {
+                  const char* who, int zero_N = 0) {
   MDSEG_REQUIRE(dtype == MDSEG_BF16 || dtype == MDSEG_F16, "%s: inputs must be bf16 or fp16", who);
   MDSEG_REQUIRE(out_dtype == MDSEG_F32 || out_dtype == dtype, "%s: output is fp32 or the input dtype", who);
   MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && K > 0 && hw > 0 && n_b > 0 && n_b <= MDSEG_MAX_DATASETS, "%s: bad shape", who);
@@ -364,7 +382,9 @@ int launch_head16(const void* x, int dtype, int n_images, int K, int64_t hw, con
   a.out = out; a.hw = hw; a.dataset_ids = dataset_ids; a.n_datasets = n_b; a.out_cstride = out_cstride;
   a.n_kb = (K + kKB - 1) / kKB;
   a.fmt = dtype == MDSEG_F16 ? 0 : 1;
+  a.zero_N = zero_N; a.zero_NT = mdseg_head_tc16_tile(zero_N);
   int tiles_max = 0, nt_max = 0;
+  if (zero_N > 0) { tiles_max = (zero_N + a.zero_NT - 1) / a.zero_NT; nt_max = a.zero_NT; }
   for (int d = 0; d < MDSEG_MAX_DATASETS; ++d) {
     a.Nd[d] = 0; a.NTd[d] = 0;
     if (d >= n_b || bt[d] == nullptr || Nd[d] <= 0) continue;
@@ -435,8 +455,9 @@ extern "C" size_t mdseg_head_dw_tc16_workspace_bytes(int n_images, int K, int64_
   return (size_t)n_images * spi * m_tiles * n_tiles * 128 * NT * 4 + 256;
 }
 
-extern "C" int mdseg_head_dw_tc16(const void* dy16, const void* feats, int dtype, int n_images, int K, int64_t hw, int N,
-                                  float* dW, void* workspace, size_t workspace_bytes, void* stream) {
+static int head_dw_tc16_impl(const void* dy16, const void* feats, int dtype, int n_images, int K, int64_t hw, int N,
+                             const int32_t* dataset_ids, int n_datasets, float* dW, void* workspace, size_t workspace_bytes,
+                             void* stream) {
   using namespace mdseg;
   MDSEG_REQUIRE(dtype == MDSEG_BF16 || dtype == MDSEG_F16, "mdseg_head_dw_tc16: operands must be bf16 or fp16");
   MDSEG_REQUIRE(n_images > 0 && n_images <= 65535 && K > 0 && N > 0 && hw > 0 && hw % 8 == 0, "mdseg_head_dw_tc16: bad shape");
@@ -486,7 +507,36 @@ extern "C" int mdseg_head_dw_tc16(const void* dy16, const void* feats, int dtype
   MDSEG_CUDA_OK(cudaFuncSetAttribute(head_tc16_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   head_tc16_dw_kernel<<<dim3((unsigned)(a.m_tiles * a.n_tiles), (unsigned)n_slabs_total), kThreads, smem, s>>>(mapA, mapB, a);
   MDSEG_LAUNCH_OK();
-  head_tc16_dw_reduce_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256, 0, s>>>(a, n_slabs_total, N, K, dW);
+  head_tc16_dw_reduce_kernel<<<dim3((unsigned)(((long long)N * K + 255) / 256), (unsigned)(dataset_ids ? n_datasets : 1)),
+                               256, 0, s>>>(a, n_slabs_total, N, K, dataset_ids, dW);
   MDSEG_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int mdseg_head_dw_tc16(const void* dy16, const void* feats, int dtype, int n_images, int K, int64_t hw, int N,
+                                  float* dW, void* workspace, size_t workspace_bytes, void* stream) {
+  return head_dw_tc16_impl(dy16, feats, dtype, n_images, K, hw, N, nullptr, 1, dW, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t mdseg_proj_bwd_graph_tc16_workspace_bytes(int n_images, int C_uni, int64_t hw, int y_cmax) {
+  return mdseg_head_dw_tc16_workspace_bytes(n_images, C_uni, hw, y_cmax);
+}
+
+extern "C" int mdseg_proj_bwd_graph_tc16(const void* dy16, const void* x, int dtype, int n_images, int C_uni, int64_t hw,
+                                         int y_cmax, const int32_t* dataset_ids, int n_datasets, float* dG, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  MDSEG_REQUIRE(dataset_ids && n_datasets > 0 && n_datasets <= MDSEG_MAX_DATASETS,
+                "mdseg_proj_bwd_graph_tc16: dataset ids and 1..%d datasets", MDSEG_MAX_DATASETS);
+  return head_dw_tc16_impl(dy16, x, dtype, n_images, C_uni, hw, y_cmax, dataset_ids, n_datasets, dG, workspace,
+                           workspace_bytes, stream);
+}
+
+extern "C" int mdseg_proj_bwd_tc16(const void* dy16, int dtype, int n_images, int y_cmax, int64_t hw,
+                                   const void* const* graphs_tt, int ldb, int C_uni, int n_datasets,
+                                   const int32_t* dataset_ids, void* dx, int dx_dtype, void* stream) {
+  MDSEG_REQUIRE(C_uni > 0 && n_datasets > 0 && n_datasets <= MDSEG_MAX_DATASETS, "mdseg_proj_bwd_tc16: bad shape");
+  int Nd[MDSEG_MAX_DATASETS];
+  for (int d = 0; d < n_datasets; ++d) Nd[d] = C_uni;
+  return mdseg::launch_head16(dy16, dtype, n_images, y_cmax, hw, graphs_tt, ldb, Nd, n_datasets, dataset_ids, dx, C_uni,
+                              dx_dtype, (cudaStream_t)stream, "mdseg_proj_bwd_tc16", /*zero_N=*/C_uni);
 }

@@ -722,7 +722,43 @@ class _MdsProjOhemCE(torch.autograd.Function):
                        w, H, W, ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, _ptr(dx), _DT[x.dtype],
                        _ptr(ws), nbytes, _stream())
             return (dx, None, None, None, None, None, None, *([None] * n))
-        if N.lib.mdseg_up_ce_bwd_direct_is_fused(C.byref(src), h, w, H, W):
+        fused_direct = bool(N.lib.mdseg_up_ce_bwd_direct_is_fused(C.byref(src), h, w, H, W))
+        if (fused_direct and _tc16_ok(x) and Cu >= 32
+                and all(tab.g[i].dense and 8 <= Cs[i] <= 1024 for i in range(n))):
+            # 16-bit logits / features with dense graphs (AMP GNN stage, folded prototypes): d loss / d y leaves the fused
+            # kernel in the dtype of x (what autocast's backward rounds it to) and both adjoints of the projection run
+            # on the TMA-fed tcgen05 kernels — no register-staged conversion, one launch for all datasets each.
+            dy16 = torch.zeros(B, cmax, h, w, dtype=x.dtype, device=dev)  # planes >= C_ds of an image stay zero
+            dst = _src_table([dy16.data_ptr()] * n, [cmax * h * w] * n, Cs, _DT[x.dtype], False)
+            nbytes = N.lib.mdseg_up_ce_bwd_direct_workspace_bytes(C.byref(src), B, h, w, H, W)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            N.call("mdseg_up_ce_bwd_direct", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W,
+                   ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g), 1.0, C.byref(dst), _ptr(ws), nbytes,
+                   _stream())
+            if ids is None:
+                ids = torch.zeros(B, dtype=torch.int32, device=dev)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                ldb = (cmax + 7) // 8 * 8
+                nt = N.lib.mdseg_head_tc16_tile(Cu)
+                rows = (Cu + nt - 1) // nt * nt
+                ptrs, keep_t = (C.c_void_p * n)(), []
+                for i, gph in enumerate(graphs):
+                    gt = torch.zeros(rows, ldb, dtype=x.dtype, device=dev)
+                    gt[:Cu, :Cs[i]] = gph.detach().t().to(x.dtype)
+                    keep_t.append(gt)
+                    ptrs[i] = gt.data_ptr()
+                dx = torch.empty_like(x)
+                N.call("mdseg_proj_bwd_tc16", _ptr(dy16), _DT[x.dtype], B, cmax, h * w, ptrs, ldb, Cu, n, _ptr(ids),
+                       _ptr(dx), _DT[x.dtype], _stream())
+            dG = torch.empty(n, cmax, Cu, dtype=torch.float32, device=dev)
+            nb = N.lib.mdseg_proj_bwd_graph_tc16_workspace_bytes(B, Cu, h * w, cmax)
+            ws2 = torch.empty(nb, dtype=torch.uint8, device=dev)
+            N.call("mdseg_proj_bwd_graph_tc16", _ptr(dy16), _ptr(x), _DT[x.dtype], B, Cu, h * w, cmax, _ptr(ids), n,
+                   _ptr(dG), _ptr(ws2), nb, _stream())
+            dgs = [dG[i, :Cs[i]].to(graphs[i].dtype) if ctx.needs_input_grad[7 + i] else None for i in range(n)]
+            return (dx, None, None, None, None, None, None, *dgs)
+        if fused_direct:
             # the fused single-pass kernel with the identity in place of G^T: one gradient plane d loss / d y
             dyA, dyB = torch.empty_like(y), None  # only the first C_ds planes of an image are written — and read
             dst = _src_table([dyA.data_ptr()] * n, [cmax * h * w] * n, Cs, N.F32, False)
