@@ -239,8 +239,8 @@ KERNELS_PER_CALL = {"mdseg_proj_fwd_tc16": 1, "mdseg_head_fwd_tc16": 1, "mdseg_h
                     "mdseg_up_ce_bwd_direct": 3, "mdseg_proj_fwd_tc": 2, "mdseg_proj_bwd_tc": 3, "mdseg_proj_bwd_graph_tc": 2,
                     "mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
                     "mdseg_lut_remap": 1, "mdseg_confusion": 1, "mdseg_miou": 1, "mdseg_ohem_begin": 1,
-                    "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 6, "mdseg_up_ce_bwd": 1,
-                    "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 3, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
+                    "mdseg_proj_fwd": 1, "mdseg_up_ce_fwd": 1, "mdseg_ohem_select": 1, "mdseg_up_ce_bwd": 1,
+                    "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 4, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -508,7 +508,7 @@ def run_ours(args, rank, world, local_rank):
             "mdseg_confusion_images": L + 8,
         }
         if sel_mode == 0:
-            alg.pop("mdseg_ohem_select")  # threshold branch: the radix passes return at once, no loss is read
+            alg.pop("mdseg_ohem_select")  # threshold branch: the select kernel exits after the decision, no loss is read
         if args.with_aux:  # the aux heads run through the same two calls: their bytes belong to them
             aux_px = cbar * e / 16
             alg["mdseg_up_ce_fwd"] += aux_px + L + 8

@@ -10,9 +10,17 @@
 // 3-digit (11+11+10 bit) MSD radix select over the order-preserving integer
 // image of the fp32 losses — three histogram passes and one summation pass over
 // the 4 B/px loss array — which yields the k-th largest value, the number of
-// ties to take and Σ over the selected set.  All pass kernels return
-// immediately when the threshold branch was taken, so the common case costs six
-// empty launches and no host synchronisation.
+// ties to take and Σ over the selected set.
+//
+// ONE launch (round 2; round 1 queued six kernels that returned at once in the
+// common case): a cooperative grid of at most two 1024-thread CTAs per SM.  Every
+// CTA derives the branch of every segment from the forward's counters (a pure
+// function of them), CTA s publishes the result of segment s, and when no
+// segment needs the fall-back the grid exits — no grid barrier is executed.
+// Otherwise the four passes run as loops over the same virtual blocks the
+// separate kernels used, separated by grid.sync().  No host synchronisation.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace mdseg {
@@ -73,12 +81,15 @@ __global__ void begin_kernel(mdseg_ohem_state* st, int n, float thresh) {
   }
 }
 
+// branch of a segment: a pure function of the counters the forward left (ohem_ce_loss.py:25,31)
+__device__ __forceinline__ bool needs_topk(const mdseg_ohem_state* st) { return st->n_hard < st->n_valid / 16ull; }
+
 // one CTA per segment
-__global__ void __launch_bounds__(kThreads)
-decide_kernel(mdseg_ohem_state* states, unsigned* ws, float* loss_out, int* err_flag) {
-  mdseg_ohem_state* st = states + blockIdx.x;
-  unsigned* H = ws + (size_t)blockIdx.x * kPasses * kBins;
-  for (int i = threadIdx.x; i < kPasses * kBins; i += blockDim.x) H[i] = 0u;
+__device__ void decide_segment(mdseg_ohem_state* states, unsigned* ws, float* loss_out, int* err_flag, int seg) {
+  mdseg_ohem_state* st = states + seg;
+  unsigned* H = ws + (size_t)seg * kPasses * kBins;
+  if (needs_topk(st))
+    for (int i = threadIdx.x; i < kPasses * kBins; i += blockDim.x) H[i] = 0u;
   if (threadIdx.x == 0) {
     const unsigned long long n_min = st->n_valid / 16ull;  // ohem_ce_loss.py:25
     st->n_min = n_min;
@@ -90,7 +101,7 @@ decide_kernel(mdseg_ohem_state* states, unsigned* ws, float* loss_out, int* err_
       const float loss = st->n_hard ? (float)(st->sum_hard / (double)st->n_hard) : __int_as_float(0x7fc00000);
       st->loss = loss;
       st->inv_n_sel = st->n_hard ? (float)(1.0 / (double)st->n_hard) : 0.f;
-      if (loss_out) loss_out[blockIdx.x] = loss;
+      if (loss_out) loss_out[seg] = loss;
     } else {
       st->mode = 1u;
       st->sum_sel = 0.0;
@@ -100,19 +111,20 @@ decide_kernel(mdseg_ohem_state* states, unsigned* ws, float* loss_out, int* err_
   }
 }
 
+// virtual block (vbx of nbx, image img) of histogram pass PASS
 template <int PASS>
-__global__ void __launch_bounds__(kThreads)
-radix_hist_kernel(const float* __restrict__ loss_px, int64_t px_per_image, const int32_t* __restrict__ image_seg,
-                  const mdseg_ohem_state* __restrict__ states, int n_segs, unsigned* __restrict__ ws) {
-  const int img = blockIdx.y;
+__device__ void radix_hist_block(const float* __restrict__ loss_px, int64_t px_per_image,
+                                 const int32_t* __restrict__ image_seg, const mdseg_ohem_state* states, int n_segs,
+                                 unsigned* ws, int vbx, int nbx, int img) {
   const int seg = image_seg ? image_seg[img] : 0;
   if (seg < 0 || seg >= n_segs) return;
   const mdseg_ohem_state* st = states + seg;
-  if (st->mode != 1u) return;
+  if (!needs_topk(st)) return;
   unsigned* H = ws + (size_t)seg * kPasses * kBins;
 
   __shared__ unsigned sh[kBins];
   __shared__ unsigned long long res[3];
+  __syncthreads();  // the previous virtual block of this CTA has flushed sh
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0u;
   uint32_t want = 0;
   if (PASS >= 1) {
@@ -128,8 +140,7 @@ radix_hist_kernel(const float* __restrict__ loss_px, int64_t px_per_image, const
   __syncthreads();
 
   const float* src = loss_px + (int64_t)img * px_per_image;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_image;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)vbx * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)nbx * blockDim.x) {
     const uint32_t key = float_key(src[i]);
     if (PASS == 0 || prefix_of(key, PASS) == want) atomicAdd(&sh[digit_of(key, PASS)], 1u);
   }
@@ -138,19 +149,18 @@ radix_hist_kernel(const float* __restrict__ loss_px, int64_t px_per_image, const
     if (sh[i]) atomicAdd(H + PASS * kBins + i, sh[i]);
 }
 
-// Σ loss over entries strictly above the k-th value.
-__global__ void __launch_bounds__(kThreads)
-radix_sum_kernel(float* __restrict__ loss_px, int64_t px_per_image, const int32_t* __restrict__ image_seg,
-                 mdseg_ohem_state* __restrict__ states, int n_segs, const unsigned* __restrict__ ws) {
-  const int img = blockIdx.y;
+// Σ loss over entries strictly above the k-th value (virtual block vbx of nbx, image img).
+__device__ void radix_sum_block(float* __restrict__ loss_px, int64_t px_per_image, const int32_t* __restrict__ image_seg,
+                                mdseg_ohem_state* states, int n_segs, const unsigned* ws, int vbx, int nbx, int img) {
   const int seg = image_seg ? image_seg[img] : 0;
   if (seg < 0 || seg >= n_segs) return;
   mdseg_ohem_state* st = states + seg;
-  if (st->mode != 1u) return;
+  if (!needs_topk(st)) return;
   const unsigned* H = ws + (size_t)seg * kPasses * kBins;
   __shared__ unsigned long long res[3];
   __shared__ double s_sum;
   __shared__ unsigned s_cnt;
+  __syncthreads();  // the previous virtual block of this CTA is done with res / s_sum / s_cnt
   find_bucket(H, topk_k(st), res);
   uint32_t kkey = (uint32_t)res[0];
   unsigned long long k = res[1];
@@ -171,8 +181,7 @@ radix_sum_kernel(float* __restrict__ loss_px, int64_t px_per_image, const int32_
   double sum = 0.0;
   unsigned cnt = 0;
   float* src = loss_px + (int64_t)img * px_per_image;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_image;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)vbx * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)nbx * blockDim.x) {
     const float v = src[i];
     const uint32_t key = float_key(v);
     if (key > kkey) { sum += (double)v; ++cnt; }
@@ -194,17 +203,17 @@ radix_sum_kernel(float* __restrict__ loss_px, int64_t px_per_image, const int32_
 }
 
 // one CTA per segment: finish the top-k branch
-__global__ void __launch_bounds__(kThreads)
-final_kernel(mdseg_ohem_state* states, const unsigned* __restrict__ ws, float* loss_out) {
-  mdseg_ohem_state* st = states + blockIdx.x;
-  if (st->mode != 1u) return;
-  const unsigned* H = ws + (size_t)blockIdx.x * kPasses * kBins;
+__device__ void final_segment(mdseg_ohem_state* states, const unsigned* ws, float* loss_out, int seg) {
+  mdseg_ohem_state* st = states + seg;
+  if (!needs_topk(st)) return;
+  const unsigned* H = ws + (size_t)seg * kPasses * kBins;
   __shared__ unsigned long long res[3];
   const unsigned long long ktot = topk_k(st);
+  __syncthreads();
   if (ktot == 0ull) {  // nothing to select (cannot happen unless the segment is empty)
     if (threadIdx.x == 0) {
       st->n_sel = 0; st->inv_n_sel = 0.f; st->loss = __int_as_float(0x7fc00000);
-      if (loss_out) loss_out[blockIdx.x] = st->loss;
+      if (loss_out) loss_out[seg] = st->loss;
     }
     return;
   }
@@ -229,8 +238,60 @@ final_kernel(mdseg_ohem_state* states, const unsigned* __restrict__ ws, float* l
     st->sum_sel = total;
     st->loss = (float)(total / (double)ktot);
     st->inv_n_sel = (float)(1.0 / (double)ktot);
-    if (loss_out) loss_out[blockIdx.x] = st->loss;
+    if (loss_out) loss_out[seg] = st->loss;
   }
+}
+
+struct SelectArgs {
+  float* loss_px;
+  int64_t px_per_image;
+  const int32_t* image_seg;
+  mdseg_ohem_state* states;
+  unsigned* ws;
+  float* loss_out;
+  int* err_flag;
+  int n_images, n_segs, nbx;  // nbx virtual blocks per image
+};
+
+__global__ void __launch_bounds__(kThreads) ohem_select_kernel(const SelectArgs a) {
+  namespace cg = cooperative_groups;
+  // which branch: every CTA evaluates every segment; nothing has been written to the states yet
+  bool any_topk = false;
+  for (int s = 0; s < a.n_segs; ++s) any_topk |= needs_topk(a.states + s);
+  __syncthreads();  // all threads have read the counters before thread 0 of a deciding CTA writes next to them
+  for (int s = blockIdx.x; s < a.n_segs; s += gridDim.x) decide_segment(a.states, a.ws, a.loss_out, a.err_flag, s);
+  if (!any_topk || a.n_images == 0 || a.px_per_image == 0) {
+    if (any_topk)  // empty loss vector in the fall-back branch: finish with k = 0
+      for (int s = blockIdx.x; s < a.n_segs; s += gridDim.x) final_segment(a.states, a.ws, a.loss_out, s);
+    return;  // uniform over the grid: no CTA reaches a grid barrier
+  }
+  cg::grid_group grid = cg::this_grid();
+  const int n_virtual = a.nbx * a.n_images;
+  grid.sync();  // histograms zeroed, n_min / mode published
+  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
+    radix_hist_block<0>(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  grid.sync();
+  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
+    radix_hist_block<1>(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  grid.sync();
+  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
+    radix_hist_block<2>(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  grid.sync();
+  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
+    radix_sum_block(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  grid.sync();
+  for (int s = blockIdx.x; s < a.n_segs; s += gridDim.x) final_segment(a.states, a.ws, a.loss_out, s);
+}
+
+// resident CTAs of ohem_select_kernel per SM (cooperative launches must fit the chip)
+int select_ctas_per_sm() {
+  static int cached = 0;
+  if (cached == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ohem_select_kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+    cached = n > 2 ? 2 : n;
+  }
+  return cached;
 }
 
 }  // namespace
@@ -255,22 +316,21 @@ extern "C" int mdseg_ohem_select(float* loss_px, int n_images, int64_t px_per_im
   MDSEG_REQUIRE(states && workspace && n_segments > 0, "mdseg_ohem_select: null pointer");
   MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && px_per_image >= 0, "mdseg_ohem_select: bad image count");
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned* ws = (unsigned*)workspace;
-  decide_kernel<<<n_segments, kThreads, 0, s>>>(states, ws, loss_out, err_flag);
-  MDSEG_LAUNCH_OK();
-  if (n_images == 0 || px_per_image == 0) return 0;
-  MDSEG_REQUIRE(loss_px, "mdseg_ohem_select: loss_px is null");
-  // enough CTAs to fill the chip, at most one per 8 K pixels of an image
+  MDSEG_REQUIRE(n_images == 0 || px_per_image == 0 || loss_px, "mdseg_ohem_select: loss_px is null");
+  // virtual blocks: enough to fill the chip, at most one per 8 K pixels of an image
   int64_t bx = ceil_div64(px_per_image, (int64_t)kThreads * 8);
-  int64_t want = ceil_div64((int64_t)sm_count() * 2, n_images);
+  int64_t want = ceil_div64((int64_t)sm_count() * 2, n_images > 0 ? n_images : 1);
   if (bx > want) bx = want;
   if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, (unsigned)n_images);
-  radix_hist_kernel<0><<<grid, kThreads, 0, s>>>(loss_px, px_per_image, image_seg, states, n_segments, ws);
-  radix_hist_kernel<1><<<grid, kThreads, 0, s>>>(loss_px, px_per_image, image_seg, states, n_segments, ws);
-  radix_hist_kernel<2><<<grid, kThreads, 0, s>>>(loss_px, px_per_image, image_seg, states, n_segments, ws);
-  radix_sum_kernel<<<grid, kThreads, 0, s>>>(loss_px, px_per_image, image_seg, states, n_segments, ws);
-  final_kernel<<<n_segments, kThreads, 0, s>>>(states, ws, loss_out);
-  MDSEG_LAUNCH_OK();
+  SelectArgs a;
+  a.loss_px = loss_px; a.px_per_image = px_per_image; a.image_seg = image_seg; a.states = states;
+  a.ws = (unsigned*)workspace; a.loss_out = loss_out; a.err_flag = err_flag;
+  a.n_images = n_images; a.n_segs = n_segments; a.nbx = (int)bx;
+  int64_t grid = bx * (n_images > 0 ? n_images : 1);
+  if (grid < n_segments) grid = n_segments;
+  const int64_t cap = (int64_t)sm_count() * select_ctas_per_sm();
+  if (grid > cap) grid = cap;
+  void* params[] = {(void*)&a};
+  MDSEG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ohem_select_kernel, dim3((unsigned)grid), dim3(kThreads), params, 0, s));
   return 0;
 }
