@@ -863,7 +863,17 @@ __global__ void __launch_bounds__(256) mds_bwd_fixup_kernel(const Args a) {
 #ifndef MDSEG_SEG_ROWS
 #define MDSEG_SEG_ROWS 16
 #endif
-int pick_seg_rows(int h) { return h - 1 < MDSEG_SEG_ROWS ? h - 1 : MDSEG_SEG_ROWS; }
+// Small batches of row CTAs (cfg1; a few images per rank under strong scaling) would leave most SMs without a CTA at 16
+// rows per segment: halve the segment until the grid — segments x class groups of the widest dataset x images, an upper
+// bound without reading the dataset ids — reaches one CTA per SM, not below 4 rows (the seam fix-up grows with it).
+int pick_seg_rows(int h, int w, int n_images, int c_max) {
+  int sr = h - 1 < MDSEG_SEG_ROWS ? h - 1 : MDSEG_SEG_ROWS;
+  if (sr < 1) sr = 1;
+  if (!(w % 32 == 0 && w / 32 <= kMaxRowWarps)) return sr;
+  const long long per_seg = (long long)n_images * ((c_max + kCG - 1) / kCG);
+  while (sr > 4 && per_seg * ((h - 1 + sr - 1) / sr) < sm_count()) sr /= 2;
+  return sr;
+}
 
 template <typename L>
 int launch_prep(const Args& a, int n_images, cudaStream_t s) {
@@ -990,7 +1000,7 @@ extern "C" size_t mdseg_mds_bwd_workspace_bytes(const mdseg_src_table* src, cons
     return 256;
   const int c_max = src_max_c(src);
   if (fused_route(src, graphs, geom_of(h, w, H, W))) {
-    const int sr = pick_seg_rows(h);
+    const int sr = pick_seg_rows(h, w, n_images, c_max);
     const int n_seg = (h - 1 + sr - 1) / sr;
     return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W + 1024 + col5_bytes(n_images, h, w, c_max);
   }
@@ -1057,7 +1067,7 @@ extern "C" int mdseg_mds_bwd(const mdseg_src_table* src, const mdseg_graph_table
     }
   }
   a.zero_invalid = 1;
-  a.seg_rows = pick_seg_rows(h);
+  a.seg_rows = pick_seg_rows(h, w, n_images, c_max);
   a.n_seg = (h - 1 + a.seg_rows - 1) / a.seg_rows;
   a.n_strips = (w + kOwn - 1) / kOwn;
   a.c_scr = c_max;
@@ -1091,7 +1101,7 @@ extern "C" size_t mdseg_up_ce_bwd_direct_workspace_bytes(const mdseg_src_table* 
   const Geom gm = geom_of(h, w, H, W);
   const int c_max = src_max_c(src);
   if (gm.W % 16 == 0 && tma::fast_geometry(*src, gm)) {
-    const int sr = pick_seg_rows(h);
+    const int sr = pick_seg_rows(h, w, n_images, c_max);
     const int n_seg = (h - 1 + sr - 1) / sr;
     return 2 * (size_t)n_images * n_seg * c_max * w * 4 + (size_t)n_images * H * W + 1024 + col5_bytes(n_images, h, w, c_max);
   }
@@ -1169,7 +1179,7 @@ extern "C" int mdseg_up_ce_bwd_direct(const mdseg_src_table* src, const int32_t*
     a.g[i] = GraphDev{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // identity: channel = class
   }
   a.zero_invalid = 0;  // rows of images that do not belong to a head stay as the caller initialised them
-  a.seg_rows = pick_seg_rows(h);
+  a.seg_rows = pick_seg_rows(h, w, n_images, c_max);
   a.n_seg = (h - 1 + a.seg_rows - 1) / a.seg_rows;
   a.n_strips = (w + kOwn - 1) / kOwn;
   a.c_scr = c_max;

@@ -364,8 +364,14 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
                 cur_iter = self.configer.get('iter')
                 cur_iter = cur_iter % (self.gnn_iters + self.seg_iters) % self.gnn_iters
                 max_rate = float(cur_iter) / self.gnn_iters
-                ce = (max_rate * self._fused_ce(logits, target, dataset_ids, bi_graphs[0::2], 0, fold_head)
-                      + (1 - max_rate) * self._fused_ce(logits, target, dataset_ids, bi_graphs[1::2], 1, fold_head))
+                if fold_head is not None:  # hard and soft losses from one pass over the features per direction
+                    pair = ops.mds_head_proj_ohem_ce_heads(logits, fold_head, target, dataset_ids,
+                                                           [bi_graphs[0::2], bi_graphs[1::2]],
+                                                           float(self.mdsOhemCELoss.thresh), self.mdsOhemCELoss.ignore_lb)
+                    ce = max_rate * pair[0] + (1 - max_rate) * pair[1]
+                else:
+                    ce = (max_rate * self._fused_ce(logits, target, dataset_ids, bi_graphs[0::2], 0)
+                          + (1 - max_rate) * self._fused_ce(logits, target, dataset_ids, bi_graphs[1::2], 1))
                 loss = add(loss, ce)
             else:
                 if pairs:

@@ -500,7 +500,8 @@ def _src_table(bases, strides, Cs, dtype, seg_per_dataset, c_alloc=None, cmax=No
         t.base[i] = b
         t.image_stride[i] = s
         t.C[i] = c
-        t.C_alloc[i] = c_alloc if c_alloc else c
+        ca = c_alloc[i] if isinstance(c_alloc, (list, tuple)) else c_alloc
+        t.C_alloc[i] = ca if ca else c
     return t
 
 
@@ -804,11 +805,156 @@ class _MdsProjOhemCE(torch.autograd.Function):
 
 
 def mds_proj_ohem_ce(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255, cache=None, per_dataset=False):
-    """CE(upsample(project(logits_uni, graph[dataset]))) under OHEM — no host sync.  One selection over all images
+    """CE(upsample(project(logits_uni, graph[dataset]))) under OHEM.  No host synchronisation in the loss itself
+    (counting, branch decision and selection stay on the device); the ONE exception is the descriptor cache of
+    non-trainable graphs (`BipartiteGraphs`): a graph tensor it has not seen (new object, new version or new storage)
+    is copied to the host once to build its CSR / CSC lists and to pick the sparse or the dense kernels — once per
+    run for the SEG stage's fixed 0/1 graphs, every call if the caller rebuilds the tensors.  Trainable graphs and
+    folded prototypes (`assume_dense`) are never copied.  One selection over all images
     (0-dim result, MdsOhemCELoss) or, with `per_dataset`, one selection per dataset (vector [n_datasets], NaN for a
     dataset without images: OhemCELoss per dataset, lib/loss/loss_cross_datasets.py:701-708)."""
     return _MdsProjOhemCE.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
                                 bool(per_dataset), *graphs)[0]
+
+
+class _MdsProjOhemCEHeads(torch.autograd.Function):
+    """H losses MdsOhemCELoss(upsample(project(x, graphs_k[dataset]))), k < H, that share x (the GNN stage's hard / soft
+    graph pair, lib/loss/loss_cross_datasets.py:996-1004,1063-1071): ONE projection with the graphs of a dataset
+    stacked to [H * C_ds, C_uni], H fused CE / OHEM passes on the slices of y, and in the backward one adjoint and one
+    d-graph GEMM over the stacked gradient planes — x is read once per direction instead of H times and its gradient
+    is written once instead of H times and added.  Dense graphs only (tensor-core routes); `graphs` is head-major."""
+
+    @staticmethod
+    def forward(ctx, x, labels, dataset_ids, thresh, ignore, n_heads, *graphs):
+        _require_cuda(x, labels)
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            x = x.float()
+        x = x.contiguous()
+        B, Cu, h, w = x.shape
+        labels = _labels(labels)
+        H, W = labels.shape[1:]
+        dev = x.device
+        n = len(graphs) // n_heads
+        Cs = [graphs[d].shape[0] for d in range(n)]
+        labels = _compact_labels(labels, max(Cs), ignore)
+        cmax2 = n_heads * max(Cs)
+        stacked = [torch.cat([graphs[k * n + d].detach().to(torch.float32) for k in range(n_heads)], 0) for d in range(n)]
+        cache = BipartiteGraphs(assume_dense=True)
+        tab, keep = cache.table(stacked)
+        ids = _ids32(dataset_ids, B, dev)
+        ef = err_flag(dev)
+        y = torch.empty(B, cmax2, h, w, dtype=torch.float32, device=dev)
+        _proj_fwd(x, tab, ids, B, h, w, y, cmax2, None, ef, graphs=stacked)
+        P = B * H * W
+        outs, saved = [], []
+        for k in range(n_heads):
+            ymax = torch.empty(B, h, w, dtype=torch.float32, device=dev)
+            src = _src_table([y.data_ptr() + k * c * h * w * 4 for c in Cs], [cmax2 * h * w] * n, Cs, N.F32, False,
+                             c_alloc=[cmax2 - k * c for c in Cs], cmax=ymax, cmax_ready=False)
+            loss_px = torch.empty(P, dtype=torch.float32, device=dev)
+            lse_px = torch.empty(P, dtype=torch.float32, device=dev)
+            st = _new_states(1, thresh, dev)
+            N.call("mdseg_up_ce_fwd", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W, int(ignore),
+                   _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(ef), _stream())
+            outs.append(_select(loss_px, B, H * W, None, st, 1)[0])
+            saved += [loss_px, lse_px, st]
+        ctx.save_for_backward(x, labels, ids, y, *saved, *stacked)
+        ctx.meta = (int(ignore), Cs, cmax2, (h, w, H, W), n_heads, [g.dtype for g in graphs])
+        return torch.stack(outs)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ignore, Cs, cmax2, (h, w, H, W), n_heads, gdt = ctx.meta
+        n = len(Cs)
+        x, labels, ids, y = ctx.saved_tensors[:4]
+        saved = ctx.saved_tensors[4:4 + 3 * n_heads]
+        stacked = ctx.saved_tensors[4 + 3 * n_heads:]
+        B, Cu = x.shape[:2]
+        dev = x.device
+        g = _grad_scalar(grad_out, n_heads)
+        tc16 = _tc16_ok(x) and Cu >= 32 and all(8 <= n_heads * c <= 1024 for c in Cs)
+        ddt = x.dtype if tc16 else torch.float32
+        esz = 2 if tc16 else 4
+        dy = torch.zeros(B, cmax2, h, w, dtype=ddt, device=dev)  # planes past the heads of an image's dataset stay zero
+        scratch = torch.empty(1, dtype=torch.float32, device=dev)
+        for k in range(n_heads):
+            loss_px, lse_px, st = saved[3 * k:3 * k + 3]
+            src = _src_table([y.data_ptr() + k * c * h * w * 4 for c in Cs], [cmax2 * h * w] * n, Cs, N.F32, False,
+                             c_alloc=[cmax2 - k * c for c in Cs], cmax=scratch, cmax_ready=True)
+            dst = _src_table([dy.data_ptr() + k * c * h * w * esz for c in Cs], [cmax2 * h * w] * n, Cs, _DT[ddt], False)
+            nbytes = N.lib.mdseg_up_ce_bwd_direct_workspace_bytes(C.byref(src), B, h, w, H, W)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            N.call("mdseg_up_ce_bwd_direct", C.byref(src), _ptr(ids), _ptr(labels), _DT[labels.dtype], B, h, w, H, W,
+                   ignore, _ptr(loss_px), _ptr(lse_px), _ptr(st), _ptr(g[k:k + 1]), 1.0, C.byref(dst), _ptr(ws), nbytes,
+                   _stream())
+        Cs2 = [n_heads * c for c in Cs]
+        dx = None
+        if tc16:
+            ids_ = ids if ids is not None else torch.zeros(B, dtype=torch.int32, device=dev)
+            if ctx.needs_input_grad[0]:
+                ldb = (cmax2 + 7) // 8 * 8
+                nt = N.lib.mdseg_head_tc16_tile(Cu)
+                rows = (Cu + nt - 1) // nt * nt
+                ptrs, keep_t = (C.c_void_p * n)(), []
+                for i, gph in enumerate(stacked):
+                    gt = torch.zeros(rows, ldb, dtype=x.dtype, device=dev)
+                    gt[:Cu, :Cs2[i]] = gph.t().to(x.dtype)
+                    keep_t.append(gt)
+                    ptrs[i] = gt.data_ptr()
+                dx = torch.empty_like(x)
+                N.call("mdseg_proj_bwd_tc16", _ptr(dy), _DT[x.dtype], B, cmax2, h * w, ptrs, ldb, Cu, n, _ptr(ids_),
+                       _ptr(dx), _DT[x.dtype], _stream())
+            dG = torch.empty(n, cmax2, Cu, dtype=torch.float32, device=dev)
+            nb = N.lib.mdseg_proj_bwd_graph_tc16_workspace_bytes(B, Cu, h * w, cmax2)
+            ws2 = torch.empty(nb, dtype=torch.uint8, device=dev)
+            N.call("mdseg_proj_bwd_graph_tc16", _ptr(dy), _ptr(x), _DT[x.dtype], B, Cu, h * w, cmax2, _ptr(ids_), n,
+                   _ptr(dG), _ptr(ws2), nb, _stream())
+        else:
+            cache = BipartiteGraphs(assume_dense=True)
+            tab, keep = cache.table(list(stacked))
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                nb = N.lib.mdseg_proj_bwd_tc_workspace_bytes(C.byref(tab), _DT[x.dtype])
+                ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+                N.call("mdseg_proj_bwd_tc", _ptr(dy), None, cmax2, C.byref(tab), _ptr(ids), B, h, w, _ptr(dx), _DT[x.dtype],
+                       _ptr(ws), nb, _stream())
+            dG = torch.zeros(n, cmax2 * Cu, dtype=torch.float32, device=dev)
+            nb = N.lib.mdseg_proj_bwd_graph_tc_workspace_bytes(C.byref(tab), B, h, w)
+            ws2 = torch.empty(nb, dtype=torch.uint8, device=dev)
+            N.call("mdseg_proj_bwd_graph_tc", _ptr(x), _DT[x.dtype], _ptr(dy), None, cmax2, C.byref(tab), _ptr(ids), B, h, w,
+                   _ptr(dG), cmax2 * Cu, _ptr(ws2), nb, _stream())
+            dG = dG.view(n, cmax2, Cu)
+        dgs = []
+        for k in range(n_heads):
+            for d in range(n):
+                if ctx.needs_input_grad[6 + k * n + d]:
+                    dgs.append(dG[d, k * Cs[d]:(k + 1) * Cs[d]].to(gdt[k * n + d]))
+                else:
+                    dgs.append(None)
+        return (dx, None, None, None, None, None, *dgs)
+
+
+def mds_proj_ohem_ce_heads(x, labels, dataset_ids, graph_sets, thresh, ignore=255):
+    """Vector [H] of MdsOhemCELoss values, one per graph set, sharing ONE pass over x per direction (see
+    _MdsProjOhemCEHeads).  graph_sets: H lists of n_datasets dense [C_ds, C_uni] matrices (the same C_ds in every set).
+    Falls back to H independent fused losses when the stacked route does not apply (graphs that are not all in the
+    tensor-core envelope, geometry outside the fused backward)."""
+    sets = [list(gs) for gs in graph_sets]
+    n = len(sets[0])
+    B, Cu, h, w = x.shape
+    Hh, Ww = labels.shape[1:]
+    Cs = [g.shape[0] for g in sets[0]]
+    ok = (len(sets) > 1 and all(len(gs) == n and [g.shape[0] for g in gs] == Cs for gs in sets)
+          and all(8 <= c and len(sets) * c <= 1024 for c in Cs) and Cu >= 32 and x.is_cuda)
+    if ok:
+        probe = _src_table([x.data_ptr() & ~15] * n, [4 * h * w] * n, Cs, N.F32, False, cmax=x)
+        ok = bool(N.lib.mdseg_up_ce_bwd_direct_is_fused(C.byref(probe), h, w, Hh, Ww))
+    if not ok:
+        return torch.stack([mds_proj_ohem_ce(x, labels, dataset_ids, gs, thresh, ignore,
+                                             BipartiteGraphs(assume_dense=all(g.requires_grad for g in gs)))
+                            for gs in sets])
+    flat = [g for gs in sets for g in gs]
+    return _MdsProjOhemCEHeads.apply(x, labels, dataset_ids, float(thresh), int(ignore), len(sets), *flat)
 
 
 def fold_prototypes(graphs, proto):
@@ -839,6 +985,13 @@ def mds_head_proj_ohem_ce(feats, proto, labels, dataset_ids, graphs, thresh, ign
     forward, d feats and d W_d on the tcgen05 kernels, no unified-logits tensor."""
     return mds_proj_ohem_ce(feats, labels, dataset_ids, fold_prototypes(graphs, proto), thresh, ignore,
                             cache or _folded_cache(), per_dataset)
+
+
+def mds_head_proj_ohem_ce_heads(feats, proto, labels, dataset_ids, graph_sets, thresh, ignore=255):
+    """mds_proj_ohem_ce_heads on the features with every graph set folded into the prototypes: the GNN stage's hard and
+    soft losses (loss_cross_datasets.py:971,996-1004,1063-1071) from ONE pass over the features per direction."""
+    return mds_proj_ohem_ce_heads(feats, labels, dataset_ids, [fold_prototypes(gs, proto) for gs in graph_sets], thresh,
+                                  ignore)
 
 
 def mds_head_proj_ce_mean(feats, proto, labels, dataset_ids, graphs, ignore=255, cache=None):
@@ -947,7 +1100,8 @@ class _MdsNLLPlus(torch.autograd.Function):
 
 def mds_nll_plus(logits_uni, labels, dataset_ids, graphs, thresh, ignore=255, cache=None):
     """mean over the OHEM set of -log(upsample(G_d softmax(logits_uni)))[label]: MdsOhemNLLPlusLoss.forward
-    (lib/loss/ohem_ce_loss.py:104-146) for a whole multi-dataset batch, no host sync."""
+    (lib/loss/ohem_ce_loss.py:104-146) for a whole multi-dataset batch; host synchronisation only on a miss of the
+    graph-descriptor cache (see mds_proj_ohem_ce)."""
     return _MdsNLLPlus.apply(logits_uni, labels, dataset_ids, float(thresh), int(ignore), cache or _default_graphs,
                              *graphs)
 

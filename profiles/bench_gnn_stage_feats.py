@@ -59,15 +59,23 @@ routes = {
     "unfolded": lambda f, p, gs: ops.mds_proj_ohem_ce(ops.prototype_head(f, p), labels, ids_t, gs, thresh),
     "folded": lambda f, p, gs: ops.mds_head_proj_ohem_ce(f, p, labels, ids_t, gs, thresh),
     "eager": eager,
+    # the (hard, soft) graph pair of the GNN stage, blended 0.5 / 0.5 (:1063-1071): two folded losses, or one stacked
+    # projection per direction (ops.mds_head_proj_ohem_ce_heads)
+    "pair, two folded losses": lambda f, p, gs: 0.5 * ops.mds_head_proj_ohem_ce(f, p, labels, ids_t, gs, thresh)
+    + 0.5 * ops.mds_head_proj_ohem_ce(f, p, labels, ids_t, gs2, thresh),
+    "pair, stacked heads": lambda f, p, gs: ops.mds_head_proj_ohem_ce_heads(f, p, labels, ids_t, [gs, gs2], thresh).mean(),
 }
+if os.environ.get("GNN_ROUTES"):
+    routes = {k: v for k, v in routes.items() if any(t in k for t in os.environ["GNN_ROUTES"].split(","))}
 for dt in (torch.float32, torch.bfloat16):
     feats = torch.randn(B, K, h, w, generator=g, device=dev).to(dt).requires_grad_(True)
     proto = (torch.randn(Cu, K, generator=g, device=dev) * 0.1).requires_grad_(True)
     graphs = [torch.softmax(torch.randn(c, Cu, generator=g, device=dev) * 4, dim=0).requires_grad_(True) for c in n_cats]
+    gs2 = [torch.softmax(torch.randn(c, Cu, generator=g, device=dev), dim=0).requires_grad_(True) for c in n_cats]
     for name, fn in routes.items():
         def step():
             feats.grad = None; proto.grad = None
-            for m in graphs: m.grad = None
+            for m in graphs + gs2: m.grad = None
             loss = fn(feats, proto, graphs)
             loss.backward()
             return loss
