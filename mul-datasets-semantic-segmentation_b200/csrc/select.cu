@@ -29,6 +29,7 @@ namespace {
 constexpr int kBins = 2048;
 constexpr int kPasses = 3;
 constexpr int kThreads = 1024;
+constexpr int kRep = 4;  // replicas of the CTA's histogram (warp w counts into replica w % kRep): hot bins are hot for every warp
 
 __device__ __forceinline__ unsigned long long topk_k(const mdseg_ohem_state* st) {
   unsigned long long k = st->n_min;
@@ -111,21 +112,23 @@ __device__ void decide_segment(mdseg_ohem_state* states, unsigned* ws, float* lo
   }
 }
 
-// virtual block (vbx of nbx, image img) of histogram pass PASS
+// Histogram pass PASS over a run of consecutive images of one segment (pixels [p0, p0 + px_per_image) of loss_px):
+// this CTA's interleaved share (vbx of nbx).  A run, not an image, is the unit: 148 CTAs x 1024 threads x 8 values
+// sweep 1.2 M values at a time, and per 2 M-pixel image the ragged last sweep left a third of the CTAs waiting at the
+// grid barrier.
 template <int PASS>
-__device__ void radix_hist_block(const float* __restrict__ loss_px, int64_t px_per_image,
-                                 const int32_t* __restrict__ image_seg, const mdseg_ohem_state* states, int n_segs,
-                                 unsigned* ws, int vbx, int nbx, int img) {
-  const int seg = image_seg ? image_seg[img] : 0;
+__device__ void radix_hist_block(const float* __restrict__ loss_px, int64_t p0, int64_t px_per_image, int seg,
+                                 const mdseg_ohem_state* states, int n_segs, unsigned* ws, int vbx, int nbx,
+                                 unsigned* sh /*[kRep * kBins] shared*/) {
   if (seg < 0 || seg >= n_segs) return;
   const mdseg_ohem_state* st = states + seg;
   if (!needs_topk(st)) return;
   unsigned* H = ws + (size_t)seg * kPasses * kBins;
 
-  __shared__ unsigned sh[kBins];
+  unsigned* mine = sh + ((threadIdx.x >> 5) & (kRep - 1)) * kBins;
   __shared__ unsigned long long res[3];
   __syncthreads();  // the previous virtual block of this CTA has flushed sh
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0u;
+  for (int i = threadIdx.x; i < kRep * kBins; i += blockDim.x) sh[i] = 0u;
   uint32_t want = 0;
   if (PASS >= 1) {
     find_bucket(H, topk_k(st), res);
@@ -139,20 +142,58 @@ __device__ void radix_hist_block(const float* __restrict__ loss_px, int64_t px_p
   }
   __syncthreads();
 
-  const float* src = loss_px + (int64_t)img * px_per_image;
-  for (int64_t i = (int64_t)vbx * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)nbx * blockDim.x) {
-    const uint32_t key = float_key(src[i]);
-    if (PASS == 0 || prefix_of(key, PASS) == want) atomicAdd(&sh[digit_of(key, PASS)], 1u);
+  // 16-byte loads, four per thread in flight (a scalar loop keeps 8 KB per SM in flight: latency-bound at 0.8 TB/s);
+  // equal digits inside a warp are counted once (match.any): confident nets put most losses into a handful of bins,
+  // and same-address shared-memory atomics serialise.
+  const float* src = loss_px + p0;
+  const bool vec = ((uintptr_t)src & 15) == 0;
+  const int64_t n4 = vec ? px_per_image / 4 : 0;
+  const int64_t step = (int64_t)nbx * blockDim.x;
+  auto count = [&](float v, bool on) {
+    const uint32_t key = float_key(v);
+    const bool take = on && (PASS == 0 || prefix_of(key, PASS) == want);
+    const unsigned d = take ? digit_of(key, PASS) : 0xffffffffu;
+    if (PASS == 0) {  // every value is counted and most share a few digits: one atomic per distinct digit of the warp
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (take && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&mine[d], (unsigned)__popc(peers));
+    } else if (take) {  // only the values inside the bucket found so far: few, and spread over its sub-digits
+      atomicAdd(&mine[d], 1u);
+    }
+  };
+  constexpr int kV = 4;  // 16-byte loads in flight per thread
+  for (int64_t i0 = (int64_t)vbx * blockDim.x; i0 < n4; i0 += kV * step) {  // warp-uniform trip count
+    float4 v[kV];
+    bool on[kV];
+#pragma unroll
+    for (int u = 0; u < kV; ++u) {
+      const int64_t i = i0 + threadIdx.x + u * step;
+      on[u] = i < n4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on[u]) v[u] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kV; ++u) {
+      count(v[u].x, on[u]); count(v[u].y, on[u]); count(v[u].z, on[u]); count(v[u].w, on[u]);
+    }
+  }
+  for (int64_t i0 = 4 * n4 + (int64_t)vbx * blockDim.x; i0 < px_per_image; i0 += step) {  // tail / unaligned images
+    const int64_t i = i0 + threadIdx.x;
+    const bool on = i < px_per_image;
+    count(on ? src[i] : 0.f, on);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kBins; i += blockDim.x)
-    if (sh[i]) atomicAdd(H + PASS * kBins + i, sh[i]);
+  {
+    unsigned tot = 0;
+#pragma unroll
+    for (int r = 0; r < kRep; ++r) tot += sh[r * kBins + i];
+    if (tot) atomicAdd(H + PASS * kBins + i, tot);
+  }
 }
 
-// Σ loss over entries strictly above the k-th value (virtual block vbx of nbx, image img).
-__device__ void radix_sum_block(float* __restrict__ loss_px, int64_t px_per_image, const int32_t* __restrict__ image_seg,
-                                mdseg_ohem_state* states, int n_segs, const unsigned* ws, int vbx, int nbx, int img) {
-  const int seg = image_seg ? image_seg[img] : 0;
+// Σ loss over entries strictly above the k-th value (same run / share as radix_hist_block).
+__device__ void radix_sum_block(float* __restrict__ loss_px, int64_t p0, int64_t px_per_image, int seg,
+                                mdseg_ohem_state* states, int n_segs, const unsigned* ws, int vbx, int nbx) {
   if (seg < 0 || seg >= n_segs) return;
   mdseg_ohem_state* st = states + seg;
   if (!needs_topk(st)) return;
@@ -180,17 +221,29 @@ __device__ void radix_sum_block(float* __restrict__ loss_px, int64_t px_per_imag
 
   double sum = 0.0;
   unsigned cnt = 0;
-  float* src = loss_px + (int64_t)img * px_per_image;
-  for (int64_t i = (int64_t)vbx * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)nbx * blockDim.x) {
-    const float v = src[i];
+  float* src = loss_px + p0;
+  const bool vec = ((uintptr_t)src & 15) == 0;
+  const int64_t n4 = vec ? px_per_image / 4 : 0;
+  const int64_t step = (int64_t)nbx * blockDim.x;
+  // hand out the ties first-come (torch.topk leaves the tie order unspecified too); losers are demoted so that the
+  // backward's `loss >= kth` test is exact and needs no atomics.  Returns the value to keep at this position.
+  auto visit = [&](float v) -> float {
     const uint32_t key = float_key(v);
     if (key > kkey) { sum += (double)v; ++cnt; }
-    else if (key == kkey) {
-      // hand out the ties first-come (torch.topk leaves the tie order
-      // unspecified too); losers are demoted so that the backward's
-      // `loss >= kth` test is exact and needs no atomics.
-      if (atomicAdd(&st->tie_taken, 1u) >= quota) src[i] = demoted;
-    }
+    else if (key == kkey && atomicAdd(&st->tie_taken, 1u) >= quota) return demoted;
+    return v;
+  };
+  for (int64_t i = (int64_t)vbx * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4* p = reinterpret_cast<float4*>(src) + i;
+    const float4 a = *p;
+    float4 r;
+    r.x = visit(a.x); r.y = visit(a.y); r.z = visit(a.z); r.w = visit(a.w);
+    if (r.x != a.x || r.y != a.y || r.z != a.z || r.w != a.w) *p = r;
+  }
+  for (int64_t i = 4 * n4 + (int64_t)vbx * blockDim.x + threadIdx.x; i < px_per_image; i += step) {
+    const float v = src[i];
+    const float r = visit(v);
+    if (r != v) src[i] = r;
   }
   sum = warp_sum(sum);
   cnt = warp_sum(cnt);
@@ -250,7 +303,7 @@ struct SelectArgs {
   unsigned* ws;
   float* loss_out;
   int* err_flag;
-  int n_images, n_segs, nbx;  // nbx virtual blocks per image
+  int n_images, n_segs;
 };
 
 __global__ void __launch_bounds__(kThreads) ohem_select_kernel(const SelectArgs a) {
@@ -265,20 +318,28 @@ __global__ void __launch_bounds__(kThreads) ohem_select_kernel(const SelectArgs 
       for (int s = blockIdx.x; s < a.n_segs; s += gridDim.x) final_segment(a.states, a.ws, a.loss_out, s);
     return;  // uniform over the grid: no CTA reaches a grid barrier
   }
+  __shared__ unsigned sh[kRep * kBins];  // the CTA's histogram replicas, reused by the three passes
   cg::grid_group grid = cg::this_grid();
-  const int n_virtual = a.nbx * a.n_images;
   grid.sync();  // histograms zeroed, n_min / mode published
-  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
-    radix_hist_block<0>(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  // runs of consecutive images of one segment (all images when image_seg == NULL): every CTA takes its interleaved
+  // share of every run
+#define MDSEG_FOR_RUNS(BODY)                                                                  \
+  for (int i0 = 0; i0 < a.n_images;) {                                                        \
+    const int seg = a.image_seg ? a.image_seg[i0] : 0;                                        \
+    int i1 = i0 + 1;                                                                          \
+    while (i1 < a.n_images && (a.image_seg ? a.image_seg[i1] : 0) == seg) ++i1;               \
+    const int64_t p0 = (int64_t)i0 * a.px_per_image, npx = (int64_t)(i1 - i0) * a.px_per_image; \
+    BODY;                                                                                     \
+    i0 = i1;                                                                                  \
+  }
+  MDSEG_FOR_RUNS(radix_hist_block<0>(a.loss_px, p0, npx, seg, a.states, a.n_segs, a.ws, blockIdx.x, gridDim.x, sh));
   grid.sync();
-  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
-    radix_hist_block<1>(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  MDSEG_FOR_RUNS(radix_hist_block<1>(a.loss_px, p0, npx, seg, a.states, a.n_segs, a.ws, blockIdx.x, gridDim.x, sh));
   grid.sync();
-  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
-    radix_hist_block<2>(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  MDSEG_FOR_RUNS(radix_hist_block<2>(a.loss_px, p0, npx, seg, a.states, a.n_segs, a.ws, blockIdx.x, gridDim.x, sh));
   grid.sync();
-  for (int v = blockIdx.x; v < n_virtual; v += gridDim.x)
-    radix_sum_block(a.loss_px, a.px_per_image, a.image_seg, a.states, a.n_segs, a.ws, v % a.nbx, a.nbx, v / a.nbx);
+  MDSEG_FOR_RUNS(radix_sum_block(a.loss_px, p0, npx, seg, a.states, a.n_segs, a.ws, blockIdx.x, gridDim.x));
+#undef MDSEG_FOR_RUNS
   grid.sync();
   for (int s = blockIdx.x; s < a.n_segs; s += gridDim.x) final_segment(a.states, a.ws, a.loss_out, s);
 }
@@ -317,7 +378,6 @@ extern "C" int mdseg_ohem_select(float* loss_px, int n_images, int64_t px_per_im
   MDSEG_REQUIRE(n_images >= 0 && n_images <= 65535 && px_per_image >= 0, "mdseg_ohem_select: bad image count");
   cudaStream_t s = (cudaStream_t)stream;
   MDSEG_REQUIRE(n_images == 0 || px_per_image == 0 || loss_px, "mdseg_ohem_select: loss_px is null");
-  // virtual blocks: enough to fill the chip, at most one per 8 K pixels of an image
   int64_t bx = ceil_div64(px_per_image, (int64_t)kThreads * 8);
   int64_t want = ceil_div64((int64_t)sm_count() * 2, n_images > 0 ? n_images : 1);
   if (bx > want) bx = want;
@@ -325,7 +385,8 @@ extern "C" int mdseg_ohem_select(float* loss_px, int n_images, int64_t px_per_im
   SelectArgs a;
   a.loss_px = loss_px; a.px_per_image = px_per_image; a.image_seg = image_seg; a.states = states;
   a.ws = (unsigned*)workspace; a.loss_out = loss_out; a.err_flag = err_flag;
-  a.n_images = n_images; a.n_segs = n_segments; a.nbx = (int)bx;
+  a.n_images = n_images; a.n_segs = n_segments;
+  // CTAs: one per 8 K values of the batch, at most the resident capacity of the chip (cooperative launch)
   int64_t grid = bx * (n_images > 0 ? n_images : 1);
   if (grid < n_segments) grid = n_segments;
   const int64_t cap = (int64_t)sm_count() * select_ctas_per_sm();
