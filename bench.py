@@ -81,8 +81,17 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's batch per GPU.  strong: the batch is split over the ranks "
                          "(SURVEY 8e: global batch 16 -> 2 images per GPU at N = 8)")
+    ap.add_argument("--shard", default="balanced", choices=["balanced", "contiguous"],
+                    help="--scaling strong: how the batch is split over the ranks.  balanced: equal image counts, images "
+                         "dealt by falling class count to the least loaded rank (dist_utils.shard_images_balanced); "
+                         "contiguous: blocks of consecutive images (both 150-class images of the cfg3 batch on one rank)")
     ap.add_argument("--pred-dtype", default="int64", choices=["int64", "int32", "uint8"],
                     help="dtype of the predictions handed to the confusion matrix (the reference's argmax gives int64)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture one whole step (LUT, loss forward, selection, backward through autograd, confusion "
+                         "matrices on the side stream, all-reduce, mIoU) into a CUDA graph and replay it in the "
+                         "device-resident timed loop: for the launch-bound regimes (strong scaling to a few images per "
+                         "GPU, cfg1), where ~25 launches per step cost more host time than the kernels take")
     ap.add_argument("--no-aux-workload", action="store_true",
                     help="skip the second named workload (the same step with the per-dataset aux heads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,7 +234,8 @@ def config_of(args, world):
         "l2": "inputs_exceed_l2 (logits %.2f GB, labels+preds %.2f GB per step)" %
               (n_img * c_uni * h * w * e / 1e9, px * (1 + L + P) / 1e9),
         "parallelism": f"dp{world} (images sharded, OHEM selection rank-local, one int64 hist all-reduce)",
-        "scaling": args.scaling,
+        "scaling": args.scaling if args.scaling == "weak" else f"strong ({args.shard} split of the batch)",
+        "cuda_graph": bool(args.cuda_graph),
         "streams": "loss fwd/select/bwd on the main stream, confusion matrices + all-reduce + mIoU on a side stream; "
                    "e2e: host->device copies of step i+1 on a copy stream beside step i",
     }
@@ -272,7 +282,11 @@ def run_ours(args, rank, world, local_rank):
         n_all = len(WORKLOADS[args.workload][2])
         if n_all % world:
             raise SystemExit(f"--scaling strong: {n_all} images do not split over {world} ranks")
-        images = list(dist_utils.shard_images(n_all, rank, world))
+        if args.shard == "balanced":
+            wl = WORKLOADS[args.workload]
+            images = dist_utils.shard_images_balanced([wl[0][d] for d in wl[2]], rank, world)
+        else:
+            images = list(dist_utils.shard_images(n_all, rank, world))
     bt = make_batch(args.workload, dev, 1234 + rank, images=images, logits=args.logits)
     bt["pred"] = bt["pred"].to({"int64": torch.int64, "int32": torch.int32, "uint8": torch.uint8}[args.pred_dtype])
     n_cats, ids, H, W = bt["n_cats"], bt["ids"], bt["H"], bt["W"]
@@ -353,10 +367,32 @@ def run_ours(args, rank, world, local_rank):
     if clocks:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph = None
+    if args.cuda_graph:
+        # every buffer of the step is static (inputs) or comes from the graph's private pool (autograd included); the
+        # library never synchronises or allocates, so the capture holds exactly the launches of one step
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            launches["n"] = 0
+            with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
+                step(bt["raw"], x, bt["pred"])
+            per_step_launches = launches["n"]
+        torch.cuda.current_stream().wait_stream(cap)
+        for _ in range(3):
+            graph.replay()
+        barrier()
+        ops.check_errors(dev)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        step(bt["raw"], x, bt["pred"])
+    if graph is not None:
+        for _ in range(args.steps):
+            graph.replay()
+        launches["n"] = per_step_launches * args.steps
+    else:
+        for _ in range(args.steps):
+            step(bt["raw"], x, bt["pred"])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

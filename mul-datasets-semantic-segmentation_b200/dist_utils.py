@@ -24,6 +24,29 @@ def shard_images(n_images, rank, world_size):
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+def shard_images_balanced(costs, rank, world_size):
+    """Image indices owned by `rank` when images differ in cost (the per-pixel work of the loss is proportional to the
+    class count of the image's dataset: 19 for a Cityscapes image, 150 for an ADE image).  Same number of images per
+    rank as `shard_images` (sizes differ by at most one), chosen greedily: images in order of falling cost, each to the
+    least loaded rank that still has room (ties: lowest rank) — the longest-processing-time rule under a cardinality
+    constraint.  Every rank computes the same assignment from the same `costs`; the result is sorted.  The reference's
+    loaders give every rank the same dataset mix (ims_per_gpu of each dataset, lib/get_dataloader.py); a split of ONE
+    mixed batch over the ranks has to balance it itself — contiguous blocks put both ADE images of a 16-image batch on
+    one of eight ranks (2.45x the mean work)."""
+    n = len(costs)
+    base, rem = divmod(n, int(world_size))
+    room = [base + (1 if r < rem else 0) for r in range(world_size)]
+    load = [0.0] * world_size
+    mine = []
+    for i in sorted(range(n), key=lambda j: (-float(costs[j]), j)):
+        r = min((q for q in range(world_size) if room[q] > 0), key=lambda q: (load[q], q))
+        room[r] -= 1
+        load[r] += float(costs[i])
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
 def allreduce_hist(hist):
     """Sum int64 confusion matrices over all ranks, in place; exact (the reference reduces a float32 matrix)."""
     if hist.dtype != torch.int64:
