@@ -15,7 +15,8 @@ import sys
 
 rep, cubin, kern = sys.argv[1:4]
 top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + (sys.argv[5] if len(sys.argv) > 5 else kern)],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, data = rows[1], rows[2:]
 iex, ismp, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
