@@ -94,6 +94,8 @@ def parse():
                          "GPU, cfg1), where ~25 launches per step cost more host time than the kernels take")
     ap.add_argument("--no-aux-workload", action="store_true",
                     help="skip the second named workload (the same step with the per-dataset aux heads)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the rank to the CPUs of its GPU's NUMA node (A/B of the e2e arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
     return ap.parse_args()
@@ -253,11 +255,39 @@ KERNELS_PER_CALL = {"mdseg_proj_fwd_tc16": 1, "mdseg_head_fwd_tc16": 1, "mdseg_h
                     "mdseg_proj_bwd": 1, "mdseg_mds_bwd": 4, "mdseg_ohem_ce_fwd": 1, "mdseg_ohem_ce_bwd": 1, "mdseg_add_planes": 1}
 
 
+_AFFINITY_BEFORE = []
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that its pinned host buffers (first touch) and its copy
+    engine's reads stay on the socket the GPU hangs off: with eight ranks on one host the H2D copies of the e2e arm
+    otherwise all read one node's DRAM.  Best effort: returns what was done for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        _AFFINITY_BEFORE.append(allowed)  # restored before the CPU baseline, which uses every host core
+        use = cpus & allowed
+        if node < 0 or not use:
+            return {"node": node, "bound": False, "why": "no NUMA node reported or no local CPU allowed"}
+        os.sched_setaffinity(0, use)
+        return {"node": node, "bound": True, "cpus": len(use), "pci": bdf}
+    except Exception as e:  # sysfs layout, permissions, torch without the pci_* properties
+        return {"bound": False, "why": repr(e)[:120]}
+
+
 def run_ours(args, rank, world, local_rank):
     from mdseg_b200 import dist_utils, native, ops  # raises if libmdseg_b200.so is missing: no fallback
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     launches = {"n": 0}
     per_call_ms = {}
     timing = {"on": False}
@@ -602,7 +632,7 @@ def run_ours(args, rank, world, local_rank):
             "config": config_of(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_ms,
-                    "h2d_gbs_per_rank": round(h2d / (e2e_ms * 1e-3) / 1e9, 1),
+                    "h2d_gbs_per_rank": round(h2d / (e2e_ms * 1e-3) / 1e9, 1), "numa": numa,
                     "bound": "host->device copy of the step's inputs (%.2f GB per rank and step over PCIe; the kernels "
                              "of a step take %.1f ms, the copy %.1f ms)" % (h2d / 1e9, ms_per_step, e2e_ms)},
             "gpu_launches": gpu_launches, "clocks": clk, "loss": loss_val, "ohem": ohem, "hist_check": hist_check,
@@ -729,6 +759,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     res = run_ours(args, rank, world, local_rank)
+    if _AFFINITY_BEFORE:
+        os.sched_setaffinity(0, _AFFINITY_BEFORE[0])
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = run_cpu(args, steps=2, warmup=1)
