@@ -458,25 +458,33 @@ def run_ours(args, rank, world, local_rank):
     # SURVEY 8d cfg3 lists them; the reference net emits every head for all images, semseg.py:326-333)
     aux_workload = None
     if aux is None and not args.no_aux_workload and args.bi_graphs == "onehot":
+        x.grad = None
+        torch.cuda.empty_cache()  # the allocator starts from the state a run of this workload alone would have: behind
+        # the main workload's cached blocks the mean of this loop was seen at 5.7, 7.7 and 20 ms in three runs while
+        # `--with-aux` alone gave 5.70 three times (allocator misses inside single steps suspected); the per-step median
+        # and maximum are reported next to the mean so that a stalled step shows
         agen = torch.Generator(device=dev).manual_seed(99 + rank)
         aux2 = [torch.randn(B, c, bt["h"], bt["w"], generator=agen, device=dev, dtype=ldt).requires_grad_(True)
                 for c in n_cats]
-        for _ in range(3):
+        for _ in range(5):
             step(bt["raw"], x, bt["pred"], aux=aux2)
         barrier()
         n_aux = max(3, min(args.steps, 10))
-        e0.record()
-        for _ in range(n_aux):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_aux + 1)]
+        evs[0].record()
+        for i in range(n_aux):
             step(bt["raw"], x, bt["pred"], aux=aux2)
-        e1.record()
+            evs[i + 1].record()
         barrier()
-        ms_aux = dist_utils.max_over_ranks(e0.elapsed_time(e1), dev) / n_aux
+        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_aux)]
+        ms_aux = dist_utils.max_over_ranks(evs[0].elapsed_time(evs[n_aux]), dev) / n_aux
         e_sz = 4 if ldt == torch.float32 else 2
         Lb = 8 if lab_dt == torch.int64 else 1
         cbar_all = sum(n_cats)  # every head is [B, C_d, h, w] over all images; rows of other datasets are only zero-filled
         bytes_aux = 3 * sum(n_cats[d] for d in ids) / len(ids) * e_sz / 16 + Lb + 20
         bytesA = 3 * bt["c_uni"] * e_sz / 16 + 2 * Lb + 20
         aux_workload = {"name": args.workload + "_with_aux", "ms_per_step": ms_aux, "steps": n_aux,
+                        "ms_per_step_median": float(np.median(per_step)), "ms_per_step_max": float(max(per_step)),
                         "value": dist_utils.whole_job_rate(px, world, ms_aux), "unit": UNIT, "loss": float(out["loss"]),
                         "alg_bytes_per_px_group_A_plus_aux": round(bytesA + bytes_aux, 2),
                         "aux_logit_bytes": int(B * cbar_all * bt["h"] * bt["w"] * e_sz)}

@@ -178,21 +178,51 @@ __global__ void __launch_bounds__(kThreads, 2) head_tc16_kernel(const __grid_con
     tc_after();
     const int n0 = nz * NT;
     TO* ob = (TO*)a.out + ((long long)b * a.out_cstride + n0) * a.hw;
-    for (int c0 = 0; c0 < NT; c0 += 16) {
-      if (n0 + c0 >= Nout) break;
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (p < a.hw) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (n0 + c0 + i < Nout) ob[(long long)(c0 + i) * a.hw + p] = from_f32<TO>(__uint_as_float(r[i]));
+    // 16 accumulator columns per TMEM load, two register sets: the load of the next 16 columns is in flight while the
+    // current ones are stored (a load + wait + 16 stores in lockstep left the four epilogue warps waiting on TMEM
+    // latency for about half of the epilogue).  The wait names the registers it releases, so no use can move above it.
+    int n_eff = Nout - n0;
+    n_eff = n_eff > NT ? NT : (n_eff + 15) & ~15;
+    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+    uint32_t ra[16], rb[16];
+#define MDSEG_H16_LD(R, C0)                                                                                            \
+  asm volatile(                                                                                                        \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+      : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]),      \
+        "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15])                        \
+      : "r"(taddr + (uint32_t)(C0)))
+#define MDSEG_H16_WAIT(R)                                                                                              \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                        \
+               : "+r"(R[0]), "+r"(R[1]), "+r"(R[2]), "+r"(R[3]), "+r"(R[4]), "+r"(R[5]), "+r"(R[6]), "+r"(R[7]),        \
+                 "+r"(R[8]), "+r"(R[9]), "+r"(R[10]), "+r"(R[11]), "+r"(R[12]), "+r"(R[13]), "+r"(R[14]), "+r"(R[15])   \
+               :: "memory")
+#define MDSEG_H16_ST(R, C0)                                                                                            \
+  if (p < a.hw) {                                                                                                      \
+    TO* o = ob + (long long)(C0) * a.hw + p;                                                                           \
+    if (n0 + (C0) + 16 <= Nout) { /* whole group inside the output: no per-column test */                              \
+      _Pragma("unroll") for (int i = 0; i < 16; ++i) { *o = from_f32<TO>(__uint_as_float(R[i])); o += a.hw; }          \
+    } else {                                                                                                           \
+      _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                                                 \
+        if (n0 + (C0) + i < Nout) *o = from_f32<TO>(__uint_as_float(R[i]));                                            \
+        o += a.hw;                                                                                                     \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }
+    if (n_eff > 0) MDSEG_H16_LD(ra, 0);
+    for (int c0 = 0; c0 < n_eff; c0 += 32) {
+      MDSEG_H16_WAIT(ra);
+      const bool has_b = c0 + 16 < n_eff;
+      if (has_b) MDSEG_H16_LD(rb, c0 + 16);
+      MDSEG_H16_ST(ra, c0);
+      if (has_b) {
+        MDSEG_H16_WAIT(rb);
+        if (c0 + 32 < n_eff) MDSEG_H16_LD(ra, c0 + 32);
+        MDSEG_H16_ST(rb, c0 + 16);
       }
     }
+#undef MDSEG_H16_LD
+#undef MDSEG_H16_WAIT
+#undef MDSEG_H16_ST
   }
   tc_before();
   __syncthreads();
