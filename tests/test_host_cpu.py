@@ -292,3 +292,29 @@ except AttributeError as e:
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:] + r.stdout
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys,
+    the steps it actually timed and the GPU arm's config object; without a CUDA device our arm refuses to run instead of
+    falling back to the CPU."""
+    import json
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["name"] == "tiny" and "workload" in d["config"] and "model" not in d["config"]
+    if not __import__("torch").cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny", "--steps", "1"],
+                           capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
