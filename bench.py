@@ -246,7 +246,7 @@ def config_of(args, world):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL = {"mdseg_proj_fwd_tc16": 1, "mdseg_head_fwd_tc16": 1, "mdseg_head_dw_tc16": 2, "mdseg_up_nll_fwd": 1,
+KERNELS_PER_CALL = {"mdseg_proj_fwd_tc16": 1, "mdseg_proj_bwd_tc16": 1, "mdseg_proj_bwd_graph_tc16": 2, "mdseg_head_fwd_tc16": 1, "mdseg_head_dw_tc16": 2, "mdseg_up_nll_fwd": 1,
                     "mdseg_up_nll_bwd": 1, "mdseg_softmax_nchw": 1, "mdseg_softmax_bwd_nchw": 1,
                     "mdseg_up_ce_bwd_direct": 3, "mdseg_proj_fwd_tc": 2, "mdseg_proj_bwd_tc": 3, "mdseg_proj_bwd_graph_tc": 2,
                     "mdseg_lut_remap_images": 1, "mdseg_confusion_images": 1, "mdseg_miou_images": 1,
@@ -576,6 +576,9 @@ def run_ours(args, rank, world, local_rank):
             "mdseg_up_ce_bwd_direct": cbar * 4 / 16 + L + 8 + cbar * 4 / 16,
             "mdseg_proj_bwd_tc": (cbar * 4 + cu * e) / 16,
             "mdseg_proj_bwd_graph_tc": (cbar * 4 + cu * e) / 16,
+            "mdseg_proj_fwd_tc16": (cu * e + cbar * 4) / 16,
+            "mdseg_proj_bwd_tc16": (cbar * e + cu * e) / 16,
+            "mdseg_proj_bwd_graph_tc16": (cbar * e + cu * e) / 16,
             "mdseg_lut_remap": 1 + L,
             "mdseg_confusion": L + 8,
             "mdseg_lut_remap_images": 1 + L,
@@ -601,7 +604,8 @@ def run_ours(args, rank, world, local_rank):
         tf_peak = None
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
             tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
-        for name in ("mdseg_proj_fwd_tc", "mdseg_proj_bwd_tc", "mdseg_proj_bwd_graph_tc"):
+        for name in ("mdseg_proj_fwd_tc", "mdseg_proj_bwd_tc", "mdseg_proj_bwd_graph_tc", "mdseg_proj_fwd_tc16",
+                     "mdseg_proj_bwd_tc16", "mdseg_proj_bwd_graph_tc16"):
             if name in per_kernel:
                 tfl = 2.0 * cu * cbar * (px / 16) / (per_kernel[name]["ms_per_step"] * 1e-3) / 1e12
                 per_kernel[name]["useful_tflops"] = round(tfl, 1)
@@ -621,7 +625,8 @@ def run_ours(args, rank, world, local_rank):
         grpA = sum(per_kernel.get(k, {}).get("ms_per_step", 0) for k in
                    ("mdseg_proj_fwd", "mdseg_up_ce_fwd", "mdseg_ohem_begin", "mdseg_ohem_select", "mdseg_up_ce_bwd",
                     "mdseg_proj_bwd", "mdseg_mds_bwd", "mdseg_proj_fwd_tc", "mdseg_up_ce_bwd_direct",
-                    "mdseg_proj_bwd_tc", "mdseg_proj_bwd_graph_tc"))
+                    "mdseg_proj_bwd_tc", "mdseg_proj_bwd_graph_tc", "mdseg_proj_fwd_tc16", "mdseg_proj_bwd_tc16",
+                    "mdseg_proj_bwd_graph_tc16"))
         bytesA = 3 * cu * e / 16 + 2 * L + 20
         if args.with_aux:  # + one pass over each image's own head forward, two backward (read + write), labels, loss
             bytesA += 3 * cbar * e / 16 + L + 20
