@@ -772,8 +772,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     res = run_ours(args, rank, world, local_rank)
-    if _AFFINITY_BEFORE:
-        os.sched_setaffinity(0, _AFFINITY_BEFORE[0])
+    if _AFFINITY_BEFORE:  # every thread of the process (OpenMP workers created meanwhile inherited the narrow mask)
+        for tid in os.listdir("/proc/self/task"):
+            try:
+                os.sched_setaffinity(int(tid), _AFFINITY_BEFORE[0])
+            except OSError:
+                pass
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = run_cpu(args, steps=2, warmup=1)
