@@ -47,7 +47,8 @@ enum {
   MDSEG_ERR_LABEL_RANGE = 1, /* label not in [0,C) and != ignore          */
   MDSEG_ERR_PRED_RANGE = 2,  /* prediction not in [0,Cb)                  */
   MDSEG_ERR_TOPK_RANGE = 4,  /* n_min larger than the number of loss px   */
-  MDSEG_ERR_DATASET_ID = 8   /* dataset id outside [0,n_datasets)         */
+  MDSEG_ERR_DATASET_ID = 8,  /* dataset id outside [0,n_datasets)         */
+  MDSEG_ERR_GRAPH_KIND = 16  /* a graph declared column-one-hot 0/1 is not */
 };
 
 #define MDSEG_MAX_DATASETS 32
@@ -480,6 +481,17 @@ int mdseg_up_nll_bwd(const mdseg_src_table* src /*host*/, const int32_t* dataset
                      int label_dtype, int n_images, int h, int w, int H, int W, int ignore, const float* loss_px,
                      const mdseg_ohem_state* states, const float* grad_out, float grad_scale,
                      const mdseg_src_table* dst /*host*/, void* stream);
+
+/* ---- a5: index lists of a column-one-hot 0/1 bi_graph, built on the device ---------------------------------
+ * The SEG stage's graphs (lib/models/ltbgnn_direct_learn.py:426-439, ClassRemap.getRemapMatrix lib/class_remap.py:
+ * 176-183) are walked as CSR / CSC lists by mdseg_proj_* and mdseg_mds_bwd.  A caller that knows the kind declares it
+ * and gets the lists without a device -> host copy of the matrix: G fp32 [C_ds, C_uni] row-major; buf:
+ * mdseg_graph_build_onehot_ints(C_ds, C_uni) ints holding, each rounded up to a multiple of 4 ints and in this order,
+ * csr_ptr [C_ds + 1], csc_ptr [C_uni + 1], csr4_ptr [C_ds + 1], csr_col [C_uni], csc_row [C_uni],
+ * csr4_col [C_uni + 3 C_ds], scratch [C_uni] (the field meanings of mdseg_sparse_graph).  A matrix with a value other
+ * than 0 / 1 or with two entries in a column sets MDSEG_ERR_GRAPH_KIND in err_flag. */
+size_t mdseg_graph_build_onehot_ints(int C_ds, int C_uni);
+int mdseg_graph_build_onehot(const float* G, int C_ds, int C_uni, int* buf, int32_t* err_flag, void* stream);
 
 /* ---- f2: the prototype head for 16-bit features on TMA + tcgen05 --------------------------------------------
  * out[b, n, p] = sum_k feats[b, k, p] * proto[n, k]: torch.einsum('bchw,nc->bnhw', feats, unify_prototype)

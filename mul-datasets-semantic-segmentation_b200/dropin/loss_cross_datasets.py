@@ -45,6 +45,12 @@ from .ohem_ce_loss import MdsOhemCELoss, MdsOhemNLLPlusLoss, OhemCELoss  # noqa:
 # Module-level so that a run can be switched back to the reference's operation order (tests exercise both).
 FOLD_PROTOTYPES = True
 
+# Non-trainable bi_graphs are copied to the host once per tensor object to build their index lists (ops.BipartiteGraphs).
+# A trainer whose SEG-stage graphs are 0/1 with at most one 1 per column AND rebuilt as new tensors every iteration can
+# set this to True: the lists are then built on the device without a copy, and a graph of another kind raises at the next
+# ops.check_errors().  Off by default because detached soft graphs are legal inputs of these classes.
+ASSUME_ONEHOT01_GRAPHS = False
+
 
 def _cfg(configer, *key, default=None):
     try:
@@ -261,7 +267,8 @@ class CrossDatasetsCELoss_AdvGNN(nn.Module):
                 cur += n
             self.M[:, cur:] = 1
         # one descriptor cache per graph set: the hard and the soft graphs of a dataset alternate in one forward
-        self._graph_cache = [ops.BipartiteGraphs(), ops.BipartiteGraphs()]
+        self._graph_cache = [ops.BipartiteGraphs(assume_onehot01=ASSUME_ONEHOT01_GRAPHS),
+                             ops.BipartiteGraphs(assume_onehot01=ASSUME_ONEHOT01_GRAPHS)]
 
     def similarity_dsb(self, proto_vecs, reduce='mean'):
         """:874-893 — entropy of the soft-max over prototype-prototype dot products."""

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmdseg_b200.so")
 F32, BF16, F16 = 0, 1, 2
 U8, I32, I64 = 10, 11, 12
 NCHW, NHWC = 0, 1
-ERR_LABEL_RANGE, ERR_PRED_RANGE, ERR_TOPK_RANGE, ERR_DATASET_ID = 1, 2, 4, 8
+ERR_LABEL_RANGE, ERR_PRED_RANGE, ERR_TOPK_RANGE, ERR_DATASET_ID, ERR_GRAPH_KIND = 1, 2, 4, 8, 16
 MAX_DATASETS = 32
 
 
@@ -122,6 +122,8 @@ SIGNATURES = {
     "mdseg_argmax_hist": (_I, [_P, _I, _L, _P, _P, _I, _P, _P, _I, _P, _P]),
     "mdseg_label_nearest": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "mdseg_label_pipeline": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "mdseg_graph_build_onehot_ints": (C.c_size_t, [_I, _I]),
+    "mdseg_graph_build_onehot": (_I, [_P, _I, _I, _P, _P, _P]),
     "mdseg_head_tc16_tile": (_I, [_I]),
     "mdseg_proj_fwd_tc16": (_I, [_P, _I, _I, _I, _L, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_int), _I, _P, _P, _I, _P]),
     "mdseg_head_dw_tc16_workspace_bytes": (C.c_size_t, [_I, _I, _L, _I]),

@@ -79,7 +79,8 @@ def check_errors(device=None):
     if v:
         flag.zero_()
         names = [n for n, bit in (("label out of range", 1), ("prediction out of range", 2),
-                                  ("top-k larger than the loss vector", 4), ("dataset id out of range", 8)) if v & bit]
+                                  ("top-k larger than the loss vector", 4), ("dataset id out of range", 8),
+                                  ("a graph declared column-one-hot 0/1 is not", 16)) if v & bit]
         raise RuntimeError("mdseg_b200 device-side data error: " + ", ".join(names))
 
 
@@ -381,9 +382,13 @@ class BipartiteGraphs:
     (``g.data[...] = ``) need an explicit ``invalidate()``.
     """
 
-    def __init__(self, dense_frac=0.25, assume_dense=False):
+    def __init__(self, dense_frac=0.25, assume_dense=False, assume_onehot01=False):
         self.dense_frac = dense_frac
         self.assume_dense = assume_dense  # every graph is a real matrix (folded prototypes): never copied to the host
+        # every non-trainable graph is 0/1 with at most one 1 per column (SEG-stage graphs, single-label remap matrices):
+        # its index lists are built on the device (mdseg_graph_build_onehot), no host copy; a graph that is not of that
+        # kind raises at the next check_errors()
+        self.assume_onehot01 = assume_onehot01
         self._cache = {}
 
     def invalidate(self):
@@ -402,6 +407,20 @@ class BipartiteGraphs:
             # trainable graph (GNN stage): dense by definition, decided without copying it to the host —
             # it changes every iteration and a D2H copy per graph per step would serialise the stream
             ent["dense"], ent["nnz"] = True, g.shape[0] * g.shape[1]
+            self._cache[i] = ent
+            return ent
+        if self.assume_onehot01:
+            c_ds, c_uni = g.shape
+            r4 = lambda k: (k + 3) & ~3
+            buf = torch.empty(N.lib.mdseg_graph_build_onehot_ints(c_ds, c_uni), dtype=torch.int32, device=dev)
+            g32 = g.detach().to(torch.float32).contiguous()
+            N.call("mdseg_graph_build_onehot", _ptr(g32), c_ds, c_uni, _ptr(buf), _ptr(err_flag(dev)), _stream())
+            o = 0
+            for name, n in (("csr_ptr", c_ds + 1), ("csc_ptr", c_uni + 1), ("csr4_ptr", c_ds + 1), ("csr_col", c_uni),
+                            ("csc_row", c_uni), ("csr4_col", c_uni + 3 * c_ds)):
+                ent[name] = buf[o:o + n]
+                o += r4(n)
+            ent.update(dense=False, nnz=c_uni, csr_val=None, csc_val=None, col_onehot=1, buf=buf)  # nnz: upper bound
             self._cache[i] = ent
             return ent
         m = g.detach().to(torch.float32).cpu().numpy()
