@@ -38,8 +38,8 @@ using namespace tma;
 constexpr int kKC = 8;                          // classes per TMA stage
 constexpr int kBoxW = 36;                       // staged columns: <= 3 alignment + 33
 constexpr int kStages = 2;
-constexpr int kStageFloats = kKC * 2 * kBoxW;   // 1152
-constexpr int kStageBytes = kStageFloats * 4;   // 4608
+constexpr int kStageFloats = kKC * 2 * kBoxW;   // 576
+constexpr int kStageBytes = kStageFloats * 4;   // 2304
 constexpr int kCG = 16;                         // classes per unit
 constexpr int kOwn28 = 28;                      // one-warp CTAs: owned columns per strip, 7 aligned groups of four (16-byte stores)
 constexpr int kOwn = kOwn28;
