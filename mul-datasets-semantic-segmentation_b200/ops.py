@@ -547,13 +547,17 @@ def _proj_fwd(x, tab, ids, B, h, w, y, cmax, ymax, ef, graphs=None):
     if (graphs is not None and x.dtype in (torch.bfloat16, torch.float16) and (h * w) % 8 == 0 and x.data_ptr() % 16 == 0
             and all(tab.g[i].dense and 8 <= tab.g[i].C_ds <= 1024 for i in range(n)) and tab.C_uni >= 32):
         ldb = (tab.C_uni + 7) // 8 * 8
-        ptrs, cds, keep = (C.c_void_p * n)(), (C.c_int * n)(), []
-        for i, g in enumerate(graphs):
+        ptrs, cds = (C.c_void_p * n)(), (C.c_int * n)()
+        rows = []
+        for g in graphs:
             nt = N.lib.mdseg_head_tc16_tile(g.shape[0])
-            gt = torch.zeros(((g.shape[0] + nt - 1) // nt) * nt, ldb, dtype=x.dtype, device=x.device)
-            gt[:g.shape[0], :tab.C_uni] = g.detach().to(x.dtype)
-            keep.append(gt)
-            ptrs[i], cds[i] = gt.data_ptr(), g.shape[0]
+            rows.append(((g.shape[0] + nt - 1) // nt) * nt)
+        gt = torch.zeros(sum(rows), ldb, dtype=x.dtype, device=x.device)  # one zero fill for all datasets
+        o = 0
+        for i, g in enumerate(graphs):
+            gt[o:o + g.shape[0], :tab.C_uni] = g.detach().to(x.dtype)
+            ptrs[i], cds[i] = gt.data_ptr() + o * ldb * gt.element_size(), g.shape[0]
+            o += rows[i]
         N.call("mdseg_proj_fwd_tc16", _ptr(x), _DT[x.dtype], B, tab.C_uni, h * w, ptrs, ldb, cds, n, _ptr(ids), _ptr(y), cmax,
                _stream())
         return
@@ -762,12 +766,11 @@ class _MdsProjOhemCE(torch.autograd.Function):
                 ldb = (cmax + 7) // 8 * 8
                 nt = N.lib.mdseg_head_tc16_tile(Cu)
                 rows = (Cu + nt - 1) // nt * nt
-                ptrs, keep_t = (C.c_void_p * n)(), []
+                ptrs = (C.c_void_p * n)()
+                gt = torch.zeros(n, rows, ldb, dtype=x.dtype, device=dev)  # one zero fill for all datasets
                 for i, gph in enumerate(graphs):
-                    gt = torch.zeros(rows, ldb, dtype=x.dtype, device=dev)
-                    gt[:Cu, :Cs[i]] = gph.detach().t().to(x.dtype)
-                    keep_t.append(gt)
-                    ptrs[i] = gt.data_ptr()
+                    gt[i, :Cu, :Cs[i]] = gph.detach().t().to(x.dtype)
+                    ptrs[i] = gt[i].data_ptr()
                 dx = torch.empty_like(x)
                 N.call("mdseg_proj_bwd_tc16", _ptr(dy16), _DT[x.dtype], B, cmax, h * w, ptrs, ldb, Cu, n, _ptr(ids),
                        _ptr(dx), _DT[x.dtype], _stream())
@@ -914,12 +917,11 @@ class _MdsProjOhemCEHeads(torch.autograd.Function):
                 ldb = (cmax2 + 7) // 8 * 8
                 nt = N.lib.mdseg_head_tc16_tile(Cu)
                 rows = (Cu + nt - 1) // nt * nt
-                ptrs, keep_t = (C.c_void_p * n)(), []
+                ptrs = (C.c_void_p * n)()
+                gt = torch.zeros(n, rows, ldb, dtype=x.dtype, device=dev)  # one zero fill for all datasets
                 for i, gph in enumerate(stacked):
-                    gt = torch.zeros(rows, ldb, dtype=x.dtype, device=dev)
-                    gt[:Cu, :Cs2[i]] = gph.t().to(x.dtype)
-                    keep_t.append(gt)
-                    ptrs[i] = gt.data_ptr()
+                    gt[i, :Cu, :Cs2[i]] = gph.t().to(x.dtype)
+                    ptrs[i] = gt[i].data_ptr()
                 dx = torch.empty_like(x)
                 N.call("mdseg_proj_bwd_tc16", _ptr(dy), _DT[x.dtype], B, cmax2, h * w, ptrs, ldb, Cu, n, _ptr(ids_),
                        _ptr(dx), _DT[x.dtype], _stream())
@@ -985,6 +987,12 @@ def fold_prototypes(graphs, proto):
     the [B, C_uni, h, w] unified logits (3 GB at cfg3) and their gradient are never formed, and the per-pixel
     contraction shrinks from K x C_uni + C_uni x C_ds to K x C_ds multiply-adds (512 x 358 + 358 x 61 -> 512 x 61)."""
     p32 = proto.to(torch.float32)
+    graphs = list(graphs)
+    if len(graphs) > 1 and all(g.shape[1] == graphs[0].shape[1] for g in graphs):
+        # one matmul for all datasets (and one per operand in the backward) instead of one per dataset: the rows of the
+        # stacked product are the per-dataset products, handed out as views
+        stacked = torch.cat([g.to(torch.float32) for g in graphs], 0) @ p32
+        return list(torch.split(stacked, [g.shape[0] for g in graphs], 0))
     return [g.to(torch.float32) @ p32 for g in graphs]
 
 
